@@ -1,0 +1,139 @@
+/*
+ * pacoh_b200.h -- C ABI of the B200-native engine for PACOH's meta-training hot path.
+ *
+ * The reference (jonasrothfuss/meta_learning_pacoh) is pure Python and has no FFI; the seam this
+ * library sits behind is where its inference objectives (L3) call the "random GP" log-density (L2).
+ * Every entry point names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch types.  All tensor pointers are DEVICE pointers to
+ *     contiguous fp32 (int32 where noted); the caller owns every buffer.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no allocation and no
+ *     host synchronisation happens inside, scratch comes from the caller-provided workspace.
+ *   - return value: PACOH_OK (0) or a negative PACOH_ERR_* code; per-matrix numerical status is
+ *     written to `info` on the device (0 clean, 1..3 jitter level used, <0 not positive definite),
+ *     mirroring gpytorch's psd_safe_cholesky jitter ladder 1e-6/1e-5/1e-4.
+ *   - parameter vectors use the reference's flat layout (meta_learn/models.py:266-277,319-323):
+ *     mean module, covariance module, noise_raw; MLP layers fc_1..fc_L,out; bias before weight;
+ *     weight row-major (out,in).  `outputscale_raw` (PACOH-MAP only) is appended last.
+ */
+#ifndef PACOH_B200_H
+#define PACOH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PACOH_ABI_VERSION 1
+#define PACOH_MAX_LAYERS 8
+
+enum {
+  PACOH_OK = 0,
+  PACOH_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, ...)            */
+  PACOH_ERR_UNSUPPORTED = -2,  /* architecture / size outside what the kernels implement     */
+  PACOH_ERR_WORKSPACE = -3,    /* workspace too small: call pacoh_workspace_bytes            */
+  PACOH_ERR_CUDA = -4          /* a CUDA runtime call failed (see pacoh_last_error)          */
+};
+
+enum { PACOH_MEAN_ZERO = 0, PACOH_MEAN_CONSTANT = 1, PACOH_MEAN_NN = 2 };
+enum { PACOH_COVAR_SE = 0, PACOH_COVAR_NN = 1 };
+enum { PACOH_SVGD_RBF = 0, PACOH_SVGD_IMQ = 1 };
+
+/* Architecture of one "vectorised GP" (meta_learn/random_gp.py:22-52 VectorizedGP.__init__;
+ * PACOH-MAP: meta_learn/GPR_meta_mll.py:207-251 with has_outputscale=1, noise_floor=1e-3). */
+typedef struct {
+  int32_t input_dim;                        /* d                                              */
+  int32_t mean_kind;                        /* PACOH_MEAN_*                                   */
+  int32_t covar_kind;                       /* PACOH_COVAR_*                                  */
+  int32_t n_mean_layers;                    /* hidden layers of the mean MLP                  */
+  int32_t mean_layers[PACOH_MAX_LAYERS];    /* their widths                                   */
+  int32_t n_kernel_layers;
+  int32_t kernel_layers[PACOH_MAX_LAYERS];
+  int32_t feature_dim;                      /* F: kernel-MLP output dim (ignored for SE: F=d) */
+  int32_t has_outputscale;                  /* 1: K = softplus(outputscale_raw) * exp(...)    */
+  float noise_floor;                        /* sigma^2 = noise_floor + softplus(noise_raw)    */
+} pacoh_arch_t;
+
+int pacoh_abi_version(void);
+const char* pacoh_last_error(void);
+
+/* Length D of one parameter vector for `arch` (RandomGPMeta.parameter_shapes, random_gp.py:186-190). */
+int64_t pacoh_param_count(const pacoh_arch_t* arch);
+
+/* Per-coordinate (mu, sigma) of the factorised Gaussian hyper-prior, written to HOST arrays of length D
+ * (_RandomGPBase.__init__, random_gp.py:118-157). */
+int pacoh_hyper_prior_params(const pacoh_arch_t* arch, float weight_prior_std, float bias_prior_std,
+                             float* mu_host, float* sigma_host);
+
+/* Scratch bytes needed by pacoh_meta_logprob_fwd_bwd for P parameter vectors, T batch tasks of n points. */
+int64_t pacoh_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n);
+
+/*
+ * Batched GP marginal log-likelihood, forward + backward, for every (particle, task) pair.
+ * Replaces RandomGPMeta._log_prob_likelihood + autograd (random_gp.py:206-219, svgd.py:15-16,
+ * GPR_meta_vi.py:221) and the PACOH-MAP loop body (GPR_meta_mll.py:109-113):
+ *
+ *   mll[p,t]      = log N(y_t | m_p(x_t), K_p(x_t,x_t) + sigma_p^2 I) / n
+ *   mll_sum[p]    = sum_t mll[p,t]                      (duplicates in task_idx count twice)
+ *   dtheta_lik    = d mll_sum[p] / d theta[p,:]         (P, D)
+ *
+ *   theta     (P, D)            parameter vectors
+ *   x         (T_total, n, d)   all tasks' normalised inputs;  y (T_total, n) targets
+ *   task_idx  (T) int32         indices into the T_total tasks, in batch order, may repeat
+ *   mll       (P, T) or NULL ;  mll_sum (P) ;  dtheta_lik (P, D) ;  info (P, T) int32 or NULL
+ */
+int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n,
+                           const float* theta, const float* x, const float* y, const int32_t* task_idx,
+                           float* mll, float* mll_sum, float* dtheta_lik, int32_t* info,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Hyper-prior log-density + combination (RandomGPMeta.log_prob, random_gp.py:179-180,221-222;
+ * CatDist.log_prob, models.py:159-181):
+ *
+ *   logp[p]      = prior_factor * sum_k logN(theta[p,k]; mu_k, sigma_k) + pre_factor * mll_sum[p]
+ *   dtheta[p,k]  = prior_factor * (-(theta[p,k]-mu_k)/sigma_k^2)       + pre_factor * dtheta_lik[p,k]
+ *
+ * mll_sum / dtheta_lik are the (all-reduced, when task-sharded) outputs of pacoh_meta_mll_fwd_bwd;
+ * pre_factor = n_h / (n_h + T_global) is computed by the caller (random_gp.py:209-212).
+ */
+int pacoh_logprob_finalize(int32_t P, int64_t D, const float* theta, const float* prior_mu,
+                           const float* prior_sigma, float prior_factor, float pre_factor,
+                           const float* mll_sum, const float* dtheta_lik, float* logp, float* dtheta,
+                           void* stream);
+
+/*
+ * SVGD direction (SVGD.phi tail + RBF_Kernel, svgd.py:18-21,32-59,103-107):
+ *   d2_ij = |theta_i|^2 + |theta_j|^2 - 2 theta_i.theta_j ;  gamma = 1/(1e-8 + 2 h^2)
+ *   bandwidth h > 0 fixed, or h <= 0: median heuristic  h^2 = median(d2 over all P*P) / (2 log(P+1))
+ *   phi = (K score + 2 gamma (rowsum(K) * theta - K theta)) / P
+ * gamma_out (1 float, device) receives gamma.  workspace: pacoh_svgd_workspace_bytes(P, D).
+ */
+int64_t pacoh_svgd_workspace_bytes(int32_t P, int64_t D);
+int pacoh_svgd_phi(int32_t P, int64_t D, const float* theta, const float* score, float bandwidth,
+                   int32_t kernel_kind, float* phi, float* gamma_out, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/*
+ * Diagonal-Gaussian VI posterior (RandomGPPosterior cov_type='diag', random_gp.py:244-263;
+ * get_neg_elbo, GPR_meta_vi.py:216-224).
+ *   sample:  theta[s,k] = loc[k] + exp(scale[k]) * eps[s,k] ;  logq[s] = sum_k logN(theta; loc, exp(scale))
+ *   grad  :  loss = -(1/S) sum_s (logp_s - prior_factor*logq_s) with g = dlogp/dtheta (S, D):
+ *            dloc[k] = -(1/S) sum_s g[s,k] ;  dscale[k] = -(1/S) sum_s g[s,k] eps[s,k] exp(scale[k]) - prior_factor
+ */
+int pacoh_vi_sample(int32_t S, int64_t D, const float* loc, const float* scale, const float* eps,
+                    float* theta, float* logq, void* stream);
+int pacoh_vi_grad(int32_t S, int64_t D, const float* scale, const float* eps, const float* g,
+                  float prior_factor, float* dloc, float* dscale, void* stream);
+
+/* FP32 FFMA micro-benchmark used by bench.py for the roofline denominator: runs `iters` dependent-chain
+ * FFMA blocks on every SM and returns the number of floating-point operations issued in *flops_out (host). */
+int pacoh_ffma_peak_launch(int32_t iters, float* sink, double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACOH_B200_H */

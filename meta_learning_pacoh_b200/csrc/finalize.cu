@@ -1,0 +1,168 @@
+// Deterministic reductions and the small elementwise kernels around the batched MLL:
+//   * sum of per-CTA parameter-gradient partials              (second stage of the mlp_bwd reduction)
+//   * sum over tasks of mll and of the GP hyper-parameter gradients
+//   * hyper-prior log-density + gradient and the final combination   (random_gp.py:179-180, 221-222;
+//                                                                     CatDist.log_prob models.py:159-181)
+//   * diagonal-Gaussian VI reparameterised sample / log q / gradient epilogue
+//                                                                    (random_gp.py:244-263, GPR_meta_vi.py:216-224)
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace pacoh {
+
+namespace {
+
+// dtheta[p, dst_off + i] = sum_c partial[c, p, i]    (fixed summation order => bitwise repeatable)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int chunks, int P, int total,
+                                       float* __restrict__ dtheta, int D, int dst_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (i >= total) return;
+  float s = 0.0f;
+  for (int c = 0; c < chunks; ++c) s += partial[((size_t)c * P + p) * total + i];
+  dtheta[(size_t)p * D + dst_off + i] = s;
+}
+
+// One CTA per particle: mll_sum[p] = sum_t mll[p,t]; hyper-parameter gradients summed over tasks.
+__global__ void reduce_hyp_kernel(GpArgs a, float* __restrict__ dtheta, float* __restrict__ mll_sum) {
+  __shared__ float red[32];
+  const int p = blockIdx.x;
+  const int H = a.F + 3;
+  const float* hyp = a.dhyp + (size_t)p * a.T * H;
+  for (int c = -1; c < H; ++c) {
+    float s = 0.0f;
+    if (c < 0) for (int t = threadIdx.x; t < a.T; t += blockDim.x) s += a.mll[(size_t)p * a.T + t];
+    else       for (int t = threadIdx.x; t < a.T; t += blockDim.x) s += hyp[(size_t)t * H + c];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) {
+        float* row = dtheta + (size_t)p * a.D;
+        if (c < 0) mll_sum[p] = v;
+        else if (c < a.F) row[a.off_ls + c] = v;
+        else if (c == a.F) row[a.off_noise] = v;
+        else if (c == a.F + 1) { if (a.has_oscale) row[a.off_oscale] = v; }
+        else if (a.mean_kind == PACOH_MEAN_CONSTANT) row[a.off_const_mean] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void logprob_finalize_kernel(int P, int64_t D, const float* __restrict__ theta, const float* __restrict__ mu,
+                                        const float* __restrict__ sigma, float prior_factor, float pre_factor,
+                                        const float* __restrict__ mll_sum, const float* __restrict__ dlik,
+                                        float* __restrict__ logp, float* __restrict__ dtheta) {
+  __shared__ float red[32];
+  const int p = blockIdx.x;
+  float lp = 0.0f;
+  for (int64_t k = threadIdx.x; k < D; k += blockDim.x) {
+    const float s = sigma[k];
+    const float zc = (theta[p * D + k] - mu[k]) / s;
+    lp += -0.5f * zc * zc - logf(s) - 0.91893853320467274178f;
+    if (dtheta != nullptr) dtheta[p * D + k] = fmaf(pre_factor, dlik[p * D + k], -prior_factor * zc / s);
+  }
+  lp = warp_sum(lp);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && logp != nullptr) logp[p] = fmaf(prior_factor, v, pre_factor * mll_sum[p]);
+  }
+}
+
+__global__ void vi_sample_kernel(int S, int64_t D, const float* __restrict__ loc, const float* __restrict__ scale,
+                                 const float* __restrict__ eps, float* __restrict__ theta, float* __restrict__ logq) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  float lq = 0.0f;
+  for (int64_t k = threadIdx.x; k < D; k += blockDim.x) {
+    const float e = eps[s * D + k], sc = scale[k];
+    theta[s * D + k] = fmaf(expf(sc), e, loc[k]);
+    lq += -0.5f * e * e - sc - 0.91893853320467274178f;
+  }
+  lq = warp_sum(lq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && logq != nullptr) logq[s] = v;
+  }
+}
+
+__global__ void vi_grad_kernel(int S, int64_t D, const float* __restrict__ scale, const float* __restrict__ eps,
+                               const float* __restrict__ g, float prior_factor, float* __restrict__ dloc,
+                               float* __restrict__ dscale) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= D) return;
+  float gl = 0.0f, gs = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const float gv = g[s * D + k];
+    gl += gv;
+    gs = fmaf(gv, eps[s * D + k], gs);
+  }
+  const float invS = 1.0f / (float)S;
+  dloc[k] = -gl * invS;
+  dscale[k] = -gs * invS * expf(scale[k]) - prior_factor;
+}
+
+}  // namespace
+
+int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,
+                           cudaStream_t st) {
+  dim3 grid((total + 255) / 256, P);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(partial, chunks, P, total, dtheta, D, dst_off);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+int launch_reduce_hyp(const GpArgs& a, float* dtheta, float* mll_sum, cudaStream_t st) {
+  reduce_hyp_kernel<<<a.P, 256, 0, st>>>(a, dtheta, mll_sum);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+}  // namespace pacoh
+
+using namespace pacoh;
+
+extern "C" int pacoh_logprob_finalize(int32_t P, int64_t D, const float* theta, const float* prior_mu,
+                                      const float* prior_sigma, float prior_factor, float pre_factor,
+                                      const float* mll_sum, const float* dtheta_lik, float* logp, float* dtheta,
+                                      void* stream) {
+  if (P < 1 || D < 1 || !theta || !prior_mu || !prior_sigma || !mll_sum || (dtheta && !dtheta_lik)) {
+    set_error("pacoh_logprob_finalize: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  logprob_finalize_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(P, D, theta, prior_mu, prior_sigma, prior_factor, pre_factor,
+                                                               mll_sum, dtheta_lik, logp, dtheta);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_vi_sample(int32_t S, int64_t D, const float* loc, const float* scale, const float* eps, float* theta,
+                               float* logq, void* stream) {
+  if (S < 1 || D < 1 || !loc || !scale || !eps || !theta) {
+    set_error("pacoh_vi_sample: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  vi_sample_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(S, D, loc, scale, eps, theta, logq);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_vi_grad(int32_t S, int64_t D, const float* scale, const float* eps, const float* g, float prior_factor,
+                             float* dloc, float* dscale, void* stream) {
+  if (S < 1 || D < 1 || !scale || !eps || !g || !dloc || !dscale) {
+    set_error("pacoh_vi_grad: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  vi_grad_kernel<<<(unsigned)((D + 255) / 256), 256, 0, (cudaStream_t)stream>>>(S, D, scale, eps, g, prior_factor, dloc, dscale);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}

@@ -1,0 +1,50 @@
+// Internal kernel-launch interfaces shared between the translation units of libpacoh_b200.
+#pragma once
+#include "common.cuh"
+
+namespace pacoh {
+
+// ---- MLP forward / backward (mlp.cu, mlp_generic.cu) -------------------------------------------------
+struct MlpArgs {
+  const float* theta;     // (P, D)
+  const float* x;         // (T_total, n, d)
+  const int* task_idx;    // (T)
+  int P, T, n, d, D;
+  NetDev net[2];          // nets handled by this launch (blockIdx.z)
+  float* out[2];          // fwd: (P, Q, out_dim)
+  const float* dout[2];   // bwd: (P, Q, out_dim)
+  float* partial[2];      // bwd: (chunks, P, net.total)
+};
+int launch_mlp_fast(const MlpArgs& a, int nets, int chunks, bool bwd, cudaStream_t st);
+int launch_mlp_generic(const MlpArgs& a, int net_index, int chunks, bool bwd, float* scratch, cudaStream_t st);
+size_t mlp_generic_scratch_floats(const NetDev& net, int P, int Q);
+
+// ---- batched GP marginal log-likelihood + analytic gradient (gp_mll.cu) --------------------------------
+struct GpArgs {
+  const float* theta;     // (P, D): lengthscale_raw, noise_raw, outputscale_raw, constant_mean are read from here
+  const float* x;         // raw inputs (covar SE uses them as features)
+  const float* y;         // (T_total, n)
+  const int* task_idx;    // (T)
+  const float* mean;      // (P, Q) or nullptr (zero / constant mean)
+  const float* feat;      // (P, Q, F) or nullptr (SE on raw inputs)
+  float* dmean;           // (P, Q) or nullptr
+  float* dfeat;           // (P, Q, F) or nullptr
+  float* mll;             // (P, T)
+  float* dhyp;            // (P, T, HYP): [dl_raw(F), dnoise_raw, doscale_raw, dconst_mean]
+  int* info;              // (P, T) or nullptr
+  int P, T, n, d, F, D;
+  int mean_kind, covar_kind, has_oscale;
+  float noise_floor;
+  int off_ls, off_noise, off_oscale, off_const_mean;
+};
+constexpr int kMaxGpN = 64;    // warp-per-matrix kernel: n <= 64
+constexpr int kMaxGpF = 16;    // feature dim
+__host__ __device__ inline int gp_hyp_stride(int F) { return F + 3; }
+int launch_gp_mll(const GpArgs& a, cudaStream_t st);
+
+// ---- reductions / elementwise (finalize.cu) ------------------------------------------------------------
+int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,
+                           cudaStream_t st);
+int launch_reduce_hyp(const GpArgs& a, float* dtheta, float* mll_sum, cudaStream_t st);
+
+}  // namespace pacoh

@@ -1,0 +1,290 @@
+"""Host side of the B200 engine: architecture descriptors, device workspaces and the autograd.Functions that
+wrap the C-ABI entry points of libpacoh_b200 (include/pacoh_b200.h).
+
+PyTorch is used here for device memory, streams and torch.distributed only; every arithmetic step of the hot path
+runs in the hand-written kernels under csrc/.  There is no CPU / eager fallback.
+
+Reference seams replaced (paths relative to the reference root):
+  RandomGPMeta.log_prob + autograd.grad      meta_learn/random_gp.py:206-222, meta_learn/svgd.py:13-16
+  SVGD.phi tail + RBF_Kernel                 meta_learn/svgd.py:18-21, 32-59
+  RandomGPPosterior.rsample / log_prob       meta_learn/random_gp.py:253-263, meta_learn/GPR_meta_vi.py:216-224
+"""
+import ctypes
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+class NotPSDError(RuntimeError):
+    """Raised when a task's kernel matrix is not positive definite even after the jitter ladder
+    (same role as gpytorch.utils.errors.NotPSDError on the reference path)."""
+
+
+_MEAN = {"zero": _lib.MEAN_ZERO, "constant": _lib.MEAN_CONSTANT, "NN": _lib.MEAN_NN}
+_COVAR = {"SE": _lib.COVAR_SE, "NN": _lib.COVAR_NN}
+
+
+@dataclass(frozen=True)
+class GPArch:
+    """Architecture of the vectorised GP prior (VectorizedGP.__init__, meta_learn/random_gp.py:22-52).
+
+    ``outputscale`` / ``noise_floor`` select the PACOH-MAP variant (gpytorch ScaleKernel and
+    GaussianLikelihood(noise_constraint=GreaterThan(1e-3)), meta_learn/GPR_meta_mll.py:54-55, 218).
+    """
+    input_dim: int
+    mean_kind: str = "NN"
+    covar_kind: str = "NN"
+    mean_layers: Tuple[int, ...] = (32, 32)
+    kernel_layers: Tuple[int, ...] = (32, 32)
+    feature_dim: int = 2
+    outputscale: bool = False
+    noise_floor: float = 0.0
+    _cache: dict = field(default_factory=dict, compare=False, repr=False, hash=False)
+
+    def c_struct(self) -> _lib.PacohArch:
+        a = _lib.PacohArch()
+        a.input_dim = self.input_dim
+        a.mean_kind = _MEAN[self.mean_kind]
+        a.covar_kind = _COVAR[self.covar_kind]
+        assert len(self.mean_layers) <= _lib.PACOH_MAX_LAYERS and len(self.kernel_layers) <= _lib.PACOH_MAX_LAYERS
+        a.n_mean_layers = len(self.mean_layers)
+        for i, w in enumerate(self.mean_layers):
+            a.mean_layers[i] = int(w)
+        a.n_kernel_layers = len(self.kernel_layers)
+        for i, w in enumerate(self.kernel_layers):
+            a.kernel_layers[i] = int(w)
+        a.feature_dim = int(self.feature_dim)
+        a.has_outputscale = 1 if self.outputscale else 0
+        a.noise_floor = float(self.noise_floor)
+        return a
+
+    @property
+    def num_features(self) -> int:
+        return self.feature_dim if self.covar_kind == "NN" else self.input_dim
+
+    @property
+    def D(self) -> int:
+        """Flat parameter count, computed by the library (pacoh_param_count)."""
+        if "D" not in self._cache:
+            a = self.c_struct()
+            self._cache["D"] = int(check(lib.pacoh_param_count(ctypes.byref(a))))
+        return self._cache["D"]
+
+    def entries(self) -> "OrderedDict[str, Tuple[int, int]]":
+        """name -> (start, end) in the flat vector; names and order follow RandomGPMeta.parameter_shapes()
+        (meta_learn/random_gp.py:186-190, models.py:351-383, 319-323)."""
+        out, off = OrderedDict(), 0
+
+        def add(name, size):
+            nonlocal off
+            out[name] = (off, off + size)
+            off += size
+
+        def mlp(prefix, widths, out_dim):
+            prev = self.input_dim
+            for i, w in enumerate(widths):
+                add("%s.fc_%d.bias" % (prefix, i + 1), w)
+                add("%s.fc_%d.weight" % (prefix, i + 1), w * prev)
+                prev = w
+            add("%s.out.bias" % prefix, out_dim)
+            add("%s.out.weight" % prefix, out_dim * prev)
+
+        if self.mean_kind == "NN":
+            mlp("mean_nn", self.mean_layers, 1)
+        elif self.mean_kind == "constant":
+            add("constant_mean", 1)
+        if self.covar_kind == "NN":
+            mlp("kernel_nn", self.kernel_layers, self.feature_dim)
+        add("lengthscale_raw", self.num_features)
+        add("noise_raw", 1)
+        if self.outputscale:
+            add("outputscale_raw", 1)
+        assert off == self.D, (off, self.D)
+        return out
+
+    def hyper_prior(self, weight_prior_std=0.5, bias_prior_std=3.0):
+        """(mu, sigma) float32 CPU tensors of the factorised Gaussian hyper-prior (random_gp.py:118-157)."""
+        mu = np.empty(self.D, dtype=np.float32)
+        sigma = np.empty(self.D, dtype=np.float32)
+        a = self.c_struct()
+        check(lib.pacoh_hyper_prior_params(ctypes.byref(a), float(weight_prior_std), float(bias_prior_std),
+                                           mu.ctypes.data_as(ctypes.c_void_p), sigma.ctypes.data_as(ctypes.c_void_p)))
+        return torch.from_numpy(mu), torch.from_numpy(sigma)
+
+
+def pre_factor(task_sizes) -> float:
+    """n_h / (n_h + T): harmonic-mean task size over the sampled batch (meta_learn/random_gp.py:209-212)."""
+    sizes = np.asarray(task_sizes, dtype=np.float64)
+    hm = 1.0 / np.mean(1.0 / sizes)
+    return float(hm / (hm + len(sizes)))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, device):
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.device == device, "expected a contiguous fp32 tensor on %s" % device
+    return t
+
+
+class MetaMLLEngine:
+    """Device-resident task set + workspaces for the batched marginal log-likelihood (pacoh_meta_mll_fwd_bwd)."""
+
+    def __init__(self, arch: GPArch, x, y, device=None):
+        """x (T_total, n, d), y (T_total, n): normalised task data (abstract.py:224-258), uploaded once."""
+        self.arch = arch
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("the PACOH engine runs on CUDA devices only (no CPU fallback)")
+        x = torch.as_tensor(x, dtype=torch.float32)
+        y = torch.as_tensor(y, dtype=torch.float32)
+        assert x.ndim == 3 and y.ndim == 2 and x.shape[:2] == y.shape and x.shape[2] == arch.input_dim
+        self.x = x.contiguous().to(self.device)
+        self.y = y.contiguous().to(self.device)
+        self.T_total, self.n, self.d = x.shape
+        self._c_arch = arch.c_struct()
+        self._ws = {}
+
+    def _workspace(self, P, T):
+        key = (P, T)
+        if key not in self._ws:
+            nbytes = check(lib.pacoh_workspace_bytes(ctypes.byref(self._c_arch), P, T, self.n))
+            self._ws[key] = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+        return self._ws[key]
+
+    def mll_fwd_bwd(self, theta, task_idx, want_mll=True, want_info=True, out=None):
+        """theta (P, D) fp32 cuda; task_idx (T,) int32 cuda (batch order, may repeat).
+
+        Returns (mll (P, T) | None, packed, info | None) where ``packed`` is a flat fp32 buffer of P*D + P
+        floats: d mll_sum / d theta (P, D) followed by mll_sum (P) -- one buffer so that a task-sharded run
+        needs a single all-reduce.
+        """
+        theta = _f32c(theta, self.device)
+        assert task_idx.dtype == torch.int32 and task_idx.is_contiguous() and task_idx.device == self.device
+        P, D = theta.shape
+        assert D == self.arch.D, "theta has %d columns, architecture needs %d" % (D, self.arch.D)
+        T = task_idx.numel()
+        ws = self._workspace(P, T)
+        packed = out if out is not None else torch.empty(P * D + P, dtype=torch.float32, device=self.device)
+        mll = torch.empty(P, T, dtype=torch.float32, device=self.device) if want_mll else None
+        info = torch.empty(P, T, dtype=torch.int32, device=self.device) if want_info else None
+        dth_ptr = ctypes.c_void_p(packed.data_ptr())
+        sum_ptr = ctypes.c_void_p(packed.data_ptr() + 4 * P * D)
+        check(lib.pacoh_meta_mll_fwd_bwd(ctypes.byref(self._c_arch), P, T, self.n, _ptr(theta), _ptr(self.x), _ptr(self.y),
+                                         _ptr(task_idx), _ptr(mll), sum_ptr, dth_ptr, _ptr(info), _ptr(ws), ws.numel(),
+                                         _stream()))
+        return mll, packed, info
+
+
+def check_info(info):
+    """Host check of the per-matrix status (one device->host read): raises NotPSDError like the reference would."""
+    if info is not None and int(info.min().item()) < 0:
+        bad = int((info < 0).sum().item())
+        raise NotPSDError("%d task kernel matrices are not positive definite after jitter 1e-4" % bad)
+
+
+def logprob_finalize(theta, prior_mu, prior_sigma, prior_factor, pre, packed, want_grad=True):
+    """logp (P,), dtheta (P, D) from the (all-reduced) packed likelihood buffer: pacoh_logprob_finalize."""
+    P, D = theta.shape
+    logp = torch.empty(P, dtype=torch.float32, device=theta.device)
+    dtheta = torch.empty(P, D, dtype=torch.float32, device=theta.device) if want_grad else None
+    check(lib.pacoh_logprob_finalize(P, D, _ptr(theta), _ptr(prior_mu), _ptr(prior_sigma), float(prior_factor), float(pre),
+                                     ctypes.c_void_p(packed.data_ptr() + 4 * P * D), ctypes.c_void_p(packed.data_ptr()),
+                                     _ptr(logp), _ptr(dtheta), _stream()))
+    return logp, dtheta
+
+
+class MetaLogProb(torch.autograd.Function):
+    """logp_p = prior_factor * log p(theta_p) + pre_factor * sum_t mll_{p,t} with its analytic gradient.
+
+    Drop-in for ``RandomGPMeta.log_prob(params, tuples)`` followed by ``autograd.grad`` / ``backward``
+    (random_gp.py:221-222; svgd.py:15-16; GPR_meta_vi.py:221).  With ``group`` set, ``task_idx`` is this rank's
+    shard of the sampled batch and the packed (P, D+1) likelihood buffer is summed over ranks with one NCCL
+    all-reduce; ``pre`` must then be computed from the GLOBAL batch.
+    """
+
+    @staticmethod
+    def forward(ctx, theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None):
+        th = theta.detach().contiguous()
+        _, packed, info = engine.mll_fwd_bwd(th, task_idx, want_mll=False, want_info=True)
+        if group is not None:
+            torch.distributed.all_reduce(packed, group=group)
+        logp, dtheta = logprob_finalize(th, prior_mu, prior_sigma, prior_factor, pre, packed)
+        ctx.save_for_backward(dtheta)
+        ctx.info = info
+        ctx.mark_non_differentiable(info)
+        return logp, info
+
+    @staticmethod
+    def backward(ctx, grad_logp, _grad_info):
+        (dtheta,) = ctx.saved_tensors
+        return grad_logp.reshape(-1, 1) * dtheta, None, None, None, None, None, None, None
+
+
+def meta_log_prob(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None):
+    return MetaLogProb.apply(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group)
+
+
+class SVGDDirection:
+    """phi = (K s + grad K) / P on device, median heuristic included (pacoh_svgd_phi; svgd.py:12-23, 32-59)."""
+
+    def __init__(self, P, D, device, bandwidth=None, kernel="RBF"):
+        if kernel != "RBF":
+            raise NotImplementedError("only the RBF Stein kernel is implemented on the B200 path (IMQ: SURVEY 8(f).3)")
+        self.P, self.D, self.device = P, D, torch.device(device)
+        self.bandwidth = -1.0 if bandwidth is None else float(bandwidth)
+        nbytes = check(lib.pacoh_svgd_workspace_bytes(P, D))
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.gamma = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def __call__(self, theta, score, out=None):
+        theta, score = _f32c(theta, self.device), _f32c(score, self.device)
+        phi = out if out is not None else torch.empty_like(theta)
+        check(lib.pacoh_svgd_phi(self.P, self.D, _ptr(theta), _ptr(score), self.bandwidth, _lib.SVGD_RBF, _ptr(phi),
+                                 _ptr(self.gamma), _ptr(self.ws), self.ws.numel(), _stream()))
+        return phi
+
+
+def vi_sample(loc, scale, eps):
+    """theta = loc + exp(scale) * eps, logq(theta)  (random_gp.py:248, 256-263)."""
+    S, D = eps.shape
+    theta = torch.empty_like(eps)
+    logq = torch.empty(S, dtype=torch.float32, device=eps.device)
+    check(lib.pacoh_vi_sample(S, D, _ptr(loc), _ptr(scale), _ptr(eps), _ptr(theta), _ptr(logq), _stream()))
+    return theta, logq
+
+
+def vi_grad(scale, eps, g, prior_factor):
+    """Gradient of -(1/S) sum_s [logp(theta_s) - prior_factor * logq(theta_s)] w.r.t. (loc, scale), g = dlogp/dtheta."""
+    S, D = eps.shape
+    dloc = torch.empty(D, dtype=torch.float32, device=eps.device)
+    dscale = torch.empty(D, dtype=torch.float32, device=eps.device)
+    check(lib.pacoh_vi_grad(S, D, _ptr(scale), _ptr(eps), _ptr(g), float(prior_factor), _ptr(dloc), _ptr(dscale), _stream()))
+    return dloc, dscale
+
+
+def ffma_peak_tflops(iters=4096, reps=5):
+    """Measured FP32 FFMA throughput of the device (TFLOP/s): the FP32 roofline denominator reported by bench.py."""
+    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+    flops = ctypes.c_double(0.0)
+    best = 0.0
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.pacoh_ffma_peak_launch(iters, _ptr(sink), ctypes.byref(flops), _stream()))
+        e1.record()
+        e1.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -91,6 +91,16 @@ int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32_t T, int32
                            void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Forward pass of the learned mean / kernel-feature nets for every parameter vector at `npts` points
+ * (LearnedGPRegressionModel.forward's NN calls, models.py:505-514; used by the eval-mode posterior,
+ * GPR_meta_svgd.py:203-212).  x (npts, d) -> mean (P, npts) [mean_kind NN, else untouched / may be NULL],
+ * feat (P, npts, F) [covar_kind NN, else untouched / may be NULL].
+ */
+int64_t pacoh_gp_forward_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t npts);
+int pacoh_gp_forward(const pacoh_arch_t* arch, int32_t P, int32_t npts, const float* theta, const float* x,
+                     float* mean, float* feat, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Hyper-prior log-density + combination (RandomGPMeta.log_prob, random_gp.py:179-180,221-222;
  * CatDist.log_prob, models.py:159-181):
  *
@@ -128,6 +138,23 @@ int pacoh_vi_sample(int32_t S, int64_t D, const float* loc, const float* scale, 
                     float* theta, float* logq, void* stream);
 int pacoh_vi_grad(int32_t S, int64_t D, const float* scale, const float* eps, const float* g,
                   float prior_factor, float* dloc, float* dscale, void* stream);
+
+/*
+ * Fused Adam update of the (P, D) particle matrix (torch.optim.Adam semantics, no amsgrad / weight decay), replacing
+ * `particles.grad = -phi; optim.step()` (svgd.py:27-28; GPR_meta_svgd.py:217-225).  `grad_sign` = -1 feeds grad = -phi
+ * directly.  step is the 1-based step count AFTER this update.  All buffers have `count` floats, updated in place.
+ */
+int pacoh_adam_step(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg, float* exp_avg_sq,
+                    float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/*
+ * Optional per-stage device timing of pacoh_meta_mll_fwd_bwd (used by bench.py for the per-kernel roofline):
+ * enable, run calls, then read the accumulated milliseconds per stage since the last read
+ * (stages: 0 mlp_fwd, 1 gp_mll, 2 mlp_bwd, 3 reductions).  Reading synchronises the recorded events.
+ */
+#define PACOH_NUM_STAGES 4
+int pacoh_stage_timing_enable(int32_t on);
+int pacoh_stage_timing_read(float* ms_out, int32_t* calls_out);
 
 /* FP32 FFMA micro-benchmark used by bench.py for the roofline denominator: runs `iters` dependent-chain
  * FFMA blocks on every SM and returns the number of floating-point operations issued in *flops_out (host). */

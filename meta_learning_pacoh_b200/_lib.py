@@ -19,7 +19,8 @@ SVGD_RBF, SVGD_IMQ = 0, 1
 EXPORTED_SYMBOLS = [
     "pacoh_abi_version", "pacoh_last_error", "pacoh_param_count", "pacoh_hyper_prior_params",
     "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_logprob_finalize", "pacoh_svgd_workspace_bytes",
-    "pacoh_svgd_phi", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch",
+    "pacoh_svgd_phi", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
+    "pacoh_stage_timing_enable", "pacoh_stage_timing_read", "pacoh_gp_forward", "pacoh_gp_forward_workspace_bytes",
 ]
 
 
@@ -70,6 +71,16 @@ def _load():
     lib.pacoh_vi_sample.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp]
     lib.pacoh_vi_grad.restype = ctypes.c_int
     lib.pacoh_vi_grad.argtypes = [i32, i64, vp, vp, vp, f32, vp, vp, vp]
+    lib.pacoh_gp_forward_workspace_bytes.restype = i64
+    lib.pacoh_gp_forward_workspace_bytes.argtypes = [archp, i32, i32]
+    lib.pacoh_gp_forward.restype = ctypes.c_int
+    lib.pacoh_gp_forward.argtypes = [archp, i32, i32, vp, vp, vp, vp, vp, i64, vp]
+    lib.pacoh_adam_step.restype = ctypes.c_int
+    lib.pacoh_adam_step.argtypes = [i64, vp, vp, f32, vp, vp, f32, f32, f32, f32, i64, vp]
+    lib.pacoh_stage_timing_enable.restype = ctypes.c_int
+    lib.pacoh_stage_timing_enable.argtypes = [i32]
+    lib.pacoh_stage_timing_read.restype = ctypes.c_int
+    lib.pacoh_stage_timing_read.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     lib.pacoh_ffma_peak_launch.restype = ctypes.c_int
     lib.pacoh_ffma_peak_launch.argtypes = [i32, vp, ctypes.POINTER(ctypes.c_double), vp]
     return lib

@@ -132,6 +132,25 @@ static int make_plan(const pacoh_arch_t* arch, int P, int T, int n, Plan* pl) {
   return PACOH_OK;
 }
 
+// ---- optional per-stage timing (bench.py roofline): events are created lazily and reused
+struct StageTimer {
+  bool on = false;
+  static constexpr int kMaxCalls = 256;
+  cudaEvent_t ev[kMaxCalls][PACOH_NUM_STAGES + 1];
+  int created = 0, used = 0;
+};
+static StageTimer g_timer;
+
+static void stage_mark(int idx, cudaStream_t st) {
+  if (!g_timer.on || g_timer.used >= StageTimer::kMaxCalls) return;
+  if (g_timer.used >= g_timer.created) {
+    for (int s = 0; s <= PACOH_NUM_STAGES; ++s) cudaEventCreate(&g_timer.ev[g_timer.created][s]);
+    g_timer.created++;
+  }
+  cudaEventRecord(g_timer.ev[g_timer.used][idx], st);
+  if (idx == PACOH_NUM_STAGES) g_timer.used++;
+}
+
 __global__ void ffma_peak_kernel(int iters, float* sink) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
   const float m = 0.999f, c = 1e-3f;
@@ -230,7 +249,9 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
     return PACOH_OK;
   };
 
+  stage_mark(0, st);
   if ((rc = run_mlp(false)) != PACOH_OK) return rc;
+  stage_mark(1, st);
 
   GpArgs ga;
   memset(&ga, 0, sizeof(ga));
@@ -248,11 +269,74 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
   ga.off_ls = m.off_ls; ga.off_noise = m.off_noise; ga.off_oscale = m.off_oscale; ga.off_const_mean = m.off_const_mean;
   if ((rc = launch_gp_mll(ga, st)) != PACOH_OK) { if (rc == PACOH_ERR_UNSUPPORTED) set_error("GP kernel: unsupported n=%d / F=%d", n, m.F); return rc; }
 
+  stage_mark(2, st);
   if ((rc = run_mlp(true)) != PACOH_OK) return rc;
+  stage_mark(3, st);
 
   if (pl.mean_nn && (rc = launch_reduce_partials(ws + pl.off_pmean, pl.chunks, P, m.mean.total, dtheta_lik, m.D, m.mean.off_b[0], st)) != PACOH_OK) return rc;
   if (pl.kern_nn && (rc = launch_reduce_partials(ws + pl.off_pkern, pl.chunks, P, m.kern.total, dtheta_lik, m.D, m.kern.off_b[0], st)) != PACOH_OK) return rc;
-  return launch_reduce_hyp(ga, dtheta_lik, mll_sum, st);
+  rc = launch_reduce_hyp(ga, dtheta_lik, mll_sum, st);
+  stage_mark(4, st);
+  return rc;
+}
+
+extern "C" int64_t pacoh_gp_forward_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t npts) {
+  Plan pl;
+  int rc = make_plan(arch, P, 1, 1, &pl);
+  if (rc != PACOH_OK || npts < 1) return rc != PACOH_OK ? rc : PACOH_ERR_INVALID;
+  size_t gen = 0;
+  if (pl.mean_nn && !pl.mean_fast) gen = std::max(gen, mlp_generic_scratch_floats(pl.m.mean, P, npts));
+  if (pl.kern_nn && !pl.kern_fast) gen = std::max(gen, mlp_generic_scratch_floats(pl.m.kern, P, npts));
+  return (int64_t)(sizeof(float) * (gen + 64));
+}
+
+extern "C" int pacoh_gp_forward(const pacoh_arch_t* arch, int32_t P, int32_t npts, const float* theta, const float* x,
+                                float* mean, float* feat, void* workspace, int64_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(arch, P, 1, 1, &pl);
+  if (rc != PACOH_OK) return rc;
+  if (npts < 1 || !theta || !x) { set_error("pacoh_gp_forward: invalid argument"); return PACOH_ERR_INVALID; }
+  if (workspace_bytes < pacoh_gp_forward_workspace_bytes(arch, P, npts)) { set_error("pacoh_gp_forward: workspace too small"); return PACOH_ERR_WORKSPACE; }
+  const ModelDev& m = pl.m;
+  cudaStream_t st = (cudaStream_t)stream;
+  MlpArgs ma;
+  memset(&ma, 0, sizeof(ma));
+  ma.theta = theta; ma.x = x; ma.task_idx = nullptr;
+  ma.P = P; ma.T = 1; ma.n = npts; ma.d = m.d; ma.D = m.D;
+  const int chunks = mlp_chunks(P, 1, npts);
+  for (int z = 0; z < 2; ++z) {
+    const bool is_nn = z == 0 ? pl.mean_nn : pl.kern_nn;
+    float* dst = z == 0 ? mean : feat;
+    if (!is_nn || dst == nullptr) continue;
+    ma.net[0] = z == 0 ? m.mean : m.kern;
+    ma.out[0] = dst;
+    const bool fast = z == 0 ? pl.mean_fast : pl.kern_fast;
+    rc = fast ? launch_mlp_fast(ma, 1, chunks, false, st) : launch_mlp_generic(ma, 0, 1, false, (float*)workspace, st);
+    if (rc != PACOH_OK) return rc;
+  }
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_stage_timing_enable(int32_t on) {
+  g_timer.on = on != 0;
+  g_timer.used = 0;
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_stage_timing_read(float* ms_out, int32_t* calls_out) {
+  if (!ms_out) { set_error("pacoh_stage_timing_read: null output"); return PACOH_ERR_INVALID; }
+  for (int s = 0; s < PACOH_NUM_STAGES; ++s) ms_out[s] = 0.0f;
+  for (int c = 0; c < g_timer.used; ++c) {
+    PACOH_CUDA_CHECK(cudaEventSynchronize(g_timer.ev[c][PACOH_NUM_STAGES]));
+    for (int s = 0; s < PACOH_NUM_STAGES; ++s) {
+      float ms = 0.0f;
+      PACOH_CUDA_CHECK(cudaEventElapsedTime(&ms, g_timer.ev[c][s], g_timer.ev[c][s + 1]));
+      ms_out[s] += ms;
+    }
+  }
+  if (calls_out) *calls_out = g_timer.used;
+  g_timer.used = 0;
+  return PACOH_OK;
 }
 
 extern "C" int pacoh_ffma_peak_launch(int32_t iters, float* sink, double* flops_out, void* stream) {

@@ -111,6 +111,20 @@ __global__ void vi_grad_kernel(int S, int64_t D, const float* __restrict__ scale
   dscale[k] = -gs * invS * expf(scale[k]) - prior_factor;
 }
 
+// torch.optim.Adam (single tensor, no amsgrad, no weight decay): same operation order as torch/optim/adam.py.
+__global__ void adam_kernel(int64_t count, float* __restrict__ p, const float* __restrict__ g, float gsign,
+                            float* __restrict__ m, float* __restrict__ v, float beta1, float beta2, float eps,
+                            float step_size, float inv_sqrt_bc2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float gr = gsign * g[i];
+  const float mi = m[i] + (gr - m[i]) * (1.0f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gr * gr);   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  p[i] -= step_size * (mi / denom);
+}
+
 }  // namespace
 
 int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,
@@ -163,6 +177,19 @@ extern "C" int pacoh_vi_grad(int32_t S, int64_t D, const float* scale, const flo
     return PACOH_ERR_INVALID;
   }
   vi_grad_kernel<<<(unsigned)((D + 255) / 256), 256, 0, (cudaStream_t)stream>>>(S, D, scale, eps, g, prior_factor, dloc, dscale);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_adam_step(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg,
+                               float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int64_t step, void* stream) {
+  if (count < 1 || !param || !grad || !exp_avg || !exp_avg_sq || step < 1) {
+    set_error("pacoh_adam_step: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      count, param, grad, grad_sign, exp_avg, exp_avg_sq, beta1, beta2, eps, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)));
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

@@ -9,14 +9,17 @@
 //   mll  = [ -1/2 r^T Kt^-1 r - 1/2 log det Kt - n/2 log 2pi ] / n,   r = y - m
 //   dL/dKt = 1/2 (alpha alpha^T - Kt^-1),  dL/dm = alpha,             alpha = Kt^-1 r
 //
-// Data layout.  Lane i of the warp owns rows i and i+32 of the (unit-diagonal-normalised) matrix in REGISTERS
-// (NC columns each) plus the augmented column r.  The factorisation is a symmetric Gauss-Jordan sweep: at
-// step k the owner lane publishes pivot row k to shared memory, every lane reads its multiplier from that
-// row (symmetry) and applies the rank-1 update with broadcast LDS.128 operands -- one FFMA per matrix
-// entry per step, no dynamic register indexing, no bank conflicts, one __syncwarp per step.  The pivots are
-// the squared Cholesky diagonal (d_k = L_kk^2), so log det and the positive-definiteness test are the
-// Cholesky ones; after n sweeps the registers hold -Kt^-1 and the augmented column holds Kt^-1 r.
-// The Gram matrix is never stored: exp(-d2) is recomputed (MUFU.EX2) for the gradient contraction.
+// Data layout.  Lane i of the warp owns rows i and i+32 of the unit-diagonal-normalised matrix in REGISTERS (NC
+// columns each) plus the augmented column r.  The factorisation is a BLOCKED symmetric Gauss-Jordan sweep with
+// 4 pivots per block (13 blocks for n = 50):
+//   1. every lane copies its 4 block-column entries t0 (by symmetry = the 4 pivot rows) out of the register
+//      matrix (one jump-table switch, no dynamic register indexing) and publishes them to shared memory,
+//   2. after ONE __syncwarp every lane inverts the 4x4 pivot block redundantly in registers (its pivots are
+//      the squared Cholesky diagonal d_k = L_kk^2: same log det, same positive-definiteness test),
+//   3. the rank-4 update  A_i. -= w_i . T0  runs over the whole row with broadcast LDS.128 operands:
+//      416 independent FFMAs per block, no bank conflicts.
+// After all blocks the registers hold -Kt^-1 and the augmented column holds Kt^-1 r.  The Gram matrix is never
+// stored: exp(-d2) is recomputed (MUFU.EX2) for the gradient contraction.
 #include <math_constants.h>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -26,7 +29,12 @@ namespace pacoh {
 namespace {
 
 constexpr int kGpWarps = 4;
-constexpr int kRowBuf = 72;   // 64 columns + [64] augmented entry + [65] pivot
+#ifndef PACOH_GP_MINB
+#define PACOH_GP_MINB(NC) ((NC) > 32 ? 2 : 4)   // min CTAs per SM: 2 x 4 warps with the full register matrix, no spills
+#endif
+constexpr int kPubStride = 68;            // floats per published block column (64 rows + pad)
+constexpr int kPubFloats = 4 * kPubStride + 8;   // 4 columns + 4 augmented entries of the pivot rows (+ pad)
+constexpr float kFar = 1.0e18f;           // scaled feature of a padding row: exp2(-(1e18)^2) == 0 exactly
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -44,11 +52,34 @@ __device__ __forceinline__ float rcp_newton(float d) {
   return r * fmaf(-d, r, 2.0f);
 }
 
+// t[s][j] = A[s][4c + j] with a runtime block index c: a switch over compile-time register indices, so the
+// register matrix never needs dynamic indexing (read only: writes would turn every A register into a phi).
+template <int NC, int NS>
+__device__ __forceinline__ void block_columns(const float (&A)[NS][NC], float (&t)[NS][4], int c) {
+#define PACOH_BLK_CASE(I)                                              \
+  case I:                                                              \
+    if constexpr (4 * (I) < NC) {                                      \
+      _Pragma("unroll") for (int s = 0; s < NS; ++s)                   \
+          _Pragma("unroll") for (int j = 0; j < 4; ++j) {              \
+        t[s][j] = A[s][4 * (I) + j];                                   \
+      }                                                                \
+    }                                                                  \
+    break;
+  switch (c) {
+    PACOH_BLK_CASE(0) PACOH_BLK_CASE(1) PACOH_BLK_CASE(2) PACOH_BLK_CASE(3) PACOH_BLK_CASE(4) PACOH_BLK_CASE(5)
+    PACOH_BLK_CASE(6) PACOH_BLK_CASE(7) PACOH_BLK_CASE(8) PACOH_BLK_CASE(9) PACOH_BLK_CASE(10) PACOH_BLK_CASE(11)
+    PACOH_BLK_CASE(12) PACOH_BLK_CASE(13) PACOH_BLK_CASE(14) PACOH_BLK_CASE(15)
+    default: break;
+  }
+#undef PACOH_BLK_CASE
+}
+
 template <int NC, int FT>
-__global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
+__global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kernel(GpArgs a) {
   constexpr int NS = (NC + 31) / 32;
+  constexpr int NB = NC / 4;                   // pivot blocks
   constexpr int RS = ((FT + 1 + 3) / 4) * 4;   // smem feature row: FT scaled features, then alpha
-  __shared__ __align__(16) float s_row[kGpWarps][2][kRowBuf];
+  __shared__ __align__(16) float s_pub[kGpWarps][2][kPubFloats];
   __shared__ __align__(16) float s_feat[kGpWarps][NC][RS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,10 +105,10 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
   const float osc = a.has_oscale ? softplus_f(raw_os) : 1.0f;
   const float cmean = a.mean_kind == PACOH_MEAN_CONSTANT ? __ldg(th + a.off_const_mean) : 0.0f;
 
-  // ---- this lane's rows: residual and scaled features
+  // ---- this lane's rows: residual and scaled features (padding rows sit "infinitely far" away => zero Gram rows)
   float r[NS], u[NS][FT];
   bool valid[NS];
-  for (int i = lane; i < 2 * kRowBuf; i += 32) s_row[warp][0][i] = 0.0f;
+  for (int i = lane; i < 2 * kPubFloats; i += 32) s_pub[warp][0][i] = 0.0f;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const int row = lane + 32 * s;
@@ -91,7 +122,7 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
       float z = 0.0f;
       if (valid[s] && f < F)
         z = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * n + row) * a.d + f);
-      u[s][f] = z * inv_ls[f];
+      u[s][f] = valid[s] ? z * inv_ls[f] : kFar;
     }
     if (row < NC) {
 #pragma unroll
@@ -103,19 +134,20 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
   float A[NS][NC], aug[NS];
   float tot = 0.0f, rho = 0.0f, logdet2 = 0.0f;
   int status = -1;
-  const float jitter[4] = {0.0f, 1e-6f, 1e-5f, 1e-4f};   // gpytorch psd_safe_cholesky ladder (fp32)
+#pragma unroll 1
   for (int attempt = 0; attempt < 4 && status < 0; ++attempt) {
-    tot = osc + sig2 + jitter[attempt];
+    const float jit = attempt == 0 ? 0.0f : (attempt == 1 ? 1e-6f : (attempt == 2 ? 1e-5f : 1e-4f));   // gpytorch psd_safe_cholesky
+    tot = osc + sig2 + jit;
     rho = osc / tot;
-    // ---- normalised Gram  A = Kt / tot  (unit diagonal), augmented with r
+    // ---- normalised Gram  A = Kt / tot; the "+ (1 - rho)" of the unit diagonal is added when a row's block is extracted
 #pragma unroll
     for (int b = 0; b < NC; ++b) {
       if (b < n) {
         float fb[RS];
 #pragma unroll
-        for (int c = 0; c < RS / 4; ++c) {
-          const float4 v = lds4(&sf[b][4 * c]);
-          fb[4 * c] = v.x; fb[4 * c + 1] = v.y; fb[4 * c + 2] = v.z; fb[4 * c + 3] = v.w;
+        for (int c4 = 0; c4 < RS / 4; ++c4) {
+          const float4 v = lds4(&sf[b][4 * c4]);
+          fb[4 * c4] = v.x; fb[4 * c4 + 1] = v.y; fb[4 * c4 + 2] = v.z; fb[4 * c4 + 3] = v.w;
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -125,59 +157,110 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
             const float du = u[s][f] - fb[f];
             e = fmaf(-du, du, e);
           }
-          const float kv = rho * ex2_approx(e);
-          A[s][b] = valid[s] ? ((lane + 32 * s == b) ? 1.0f : kv) : 0.0f;
+          A[s][b] = rho * ex2_approx(e);
         }
       } else {
 #pragma unroll
         for (int s = 0; s < NS; ++s) A[s][b] = 0.0f;
       }
     }
+    float dadd[NS];   // deferred diagonal: real rows 1 - rho, identity padding rows (n <= row < NC) 1
 #pragma unroll
-    for (int s = 0; s < NS; ++s) aug[s] = r[s];
+    for (int s = 0; s < NS; ++s) {
+      aug[s] = r[s];
+      dadd[s] = valid[s] ? 1.0f - rho : 1.0f;
+    }
 
-    // ---- symmetric Gauss-Jordan sweep over the n pivots
+    // ---- blocked symmetric Gauss-Jordan sweep, 4 pivots per block
     bool ok = true;
     logdet2 = 0.0f;
-    for (int k = 0; k < n; ++k) {
-      float* rb = s_row[warp][k & 1];
-      if (lane == (k & 31)) {
-        if (NS == 1 || k < 32) {
+#pragma unroll 1
+    for (int c = 0; c < NB; ++c) {
+      if (4 * c >= n) break;                         // only identity padding left
+      float* pb = s_pub[warp][c & 1];
+      float t0[NS][4];
+      block_columns<NC, NS>(A, t0, c);
+      // publish the block columns (= the 4 pivot rows, by symmetry).  The pivot block's own diagonal is published
+      // minus 1: with X = B0 - I in place of B0 the uniform rank-4 update below also produces the swept values of
+      // the block columns themselves, so the register matrix never needs a dynamic-index write-back.
 #pragma unroll
-          for (int c = 0; c < NC / 4; ++c) sts4(rb + 4 * c, make_float4(A[0][4 * c], A[0][4 * c + 1], A[0][4 * c + 2], A[0][4 * c + 3]));
-          rb[64] = aug[0];
-        } else {
+      for (int s = 0; s < NS; ++s) {
+        const int rel = lane + 32 * s - 4 * c;       // position of this row inside the block (0..3) if it is a pivot row
 #pragma unroll
-          for (int c = 0; c < NC / 4; ++c)
-            sts4(rb + 4 * c, make_float4(A[NS - 1][4 * c], A[NS - 1][4 * c + 1], A[NS - 1][4 * c + 2], A[NS - 1][4 * c + 3]));
-          rb[64] = aug[NS - 1];
+        for (int j = 0; j < 4; ++j) {
+          if (rel == j) t0[s][j] += dadd[s];         // true diagonal (deferred unit-diagonal term)
+          pb[j * kPubStride + lane + 32 * s] = rel == j ? t0[s][j] - 1.0f : t0[s][j];
         }
-        const float dk = rb[k];
-        rb[65] = dk;
-        rb[k] = dk - 1.0f;   // makes the uniform update below produce A_ik <- A_ik / d  (and the pivot row / d)
+        if (rel >= 0 && rel < 4) pb[4 * kPubStride + rel] = aug[s];
       }
       __syncwarp();
-      const float dk = rb[65];
-      if (!(dk > 1e-12f)) { ok = false; break; }   // warp-uniform: not positive definite at this jitter level
-      logdet2 += lg2_approx(dk);
-      const float inv = rcp_newton(dk);
-      float fm[NS];
+      // ---- 4x4 pivot block (rows 4c..4c+3 of the published columns), inverted redundantly by every lane
+      float B[4][4];
 #pragma unroll
-      for (int s = 0; s < NS; ++s) fm[s] = -rb[lane + 32 * s] * inv;
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = lds4(pb + j * kPubStride + 4 * c);
+        B[j][0] = v.x; B[j][1] = v.y; B[j][2] = v.z; B[j][3] = v.w;
+        B[j][j] += 1.0f;
+      }
+      const float4 augB = lds4(pb + 4 * kPubStride);
 #pragma unroll
-      for (int c = 0; c < NC / 4; ++c) {
-        const float4 v = lds4(rb + 4 * c);
+      for (int q4 = 0; q4 < 4; ++q4) {               // in-register sweep: B <- -B^-1, pivots = Schur diagonals
+        const float d = B[q4][q4];
+        ok = ok && (d > 1e-12f);
+        logdet2 += lg2_approx(d);
+        const float inv = rcp_newton(d);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i == q4) continue;
+          const float f = B[i][q4] * inv;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j != q4) B[i][j] = fmaf(-f, B[q4][j], B[i][j]);
+          B[i][q4] = f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j != q4) B[q4][j] *= inv;
+        B[q4][q4] = -inv;
+      }
+      if (!ok) break;                                 // warp-uniform (every lane inverted the same block)
+      // ---- multipliers (Binv = -B): non-pivot rows w = t0 Binv; pivot rows w = e_rel - Binv[rel][:]
+      float w[NS][4];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int rel = lane + 32 * s - 4 * c;
+        const bool inb = rel >= 0 && rel < 4;
+        float uu[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uu[j] = -(t0[s][0] * B[0][j] + t0[s][1] * B[1][j] + t0[s][2] * B[2][j] + t0[s][3] * B[3][j]);
+          if (inb) uu[j] = rel == j ? 1.0f : 0.0f;   // B0[rel][:] Binv = e_rel exactly (no cond(B0) rounding)
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float uB = -(uu[0] * B[0][j] + uu[1] * B[1][j] + uu[2] * B[2][j] + uu[3] * B[3][j]);
+          w[s][j] = inb ? uu[j] - uB : uu[j];
+        }
+        aug[s] -= w[s][0] * augB.x + w[s][1] * augB.y + w[s][2] * augB.z + w[s][3] * augB.w;
+      }
+      // ---- rank-4 update of every row:  A[s][col] -= sum_j w[s][j] * X[j][col]
+      //      (a pivot row's own diagonal register ends up at  -Binv_rr + 2 - dadd : undone when the diagonal is read)
+#pragma unroll
+      for (int c4 = 0; c4 < NC / 4; ++c4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = lds4(pb + j * kPubStride + 4 * c4);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-          A[s][4 * c] = fmaf(fm[s], v.x, A[s][4 * c]);
-          A[s][4 * c + 1] = fmaf(fm[s], v.y, A[s][4 * c + 1]);
-          A[s][4 * c + 2] = fmaf(fm[s], v.z, A[s][4 * c + 2]);
-          A[s][4 * c + 3] = fmaf(fm[s], v.w, A[s][4 * c + 3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            A[s][4 * c4] = fmaf(-w[s][j], v[j].x, A[s][4 * c4]);
+            A[s][4 * c4 + 1] = fmaf(-w[s][j], v[j].y, A[s][4 * c4 + 1]);
+            A[s][4 * c4 + 2] = fmaf(-w[s][j], v[j].z, A[s][4 * c4 + 2]);
+            A[s][4 * c4 + 3] = fmaf(-w[s][j], v[j].w, A[s][4 * c4 + 3]);
+          }
         }
       }
-      const float va = rb[64];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) aug[s] = fmaf(fm[s], va, aug[s]);
     }
     __syncwarp();
     if (ok) status = attempt;
@@ -215,27 +298,25 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
   const float mll = (-0.5f * quad - 0.5f * logdet - 0.5f * (float)n * 1.83787706640934548356f) * inv_n;
   if (lane == 0) *mll_out = mll;
 
-  // ---- diagonal of the swept matrix (carries a +2 offset) and alpha broadcast rows
+  // ---- diagonal of -Khat^-1 (register index == lane: predicated copies) and alpha broadcast rows
   float dg[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     dg[s] = 0.0f;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (32 * s + j < NC && lane == j) dg[s] = A[s][(32 * s + j) < NC ? (32 * s + j) : 0];
+      if (32 * s + j < NC && lane == j) dg[s] = A[s][(32 * s + j) < NC ? (32 * s + j) : 0] - 1.0f - rho;   // - (2 - dadd)
     const int row = lane + 32 * s;
     if (row < NC) sf[row][FT] = aug[s];
   }
   __syncwarp();
 
   // ---- gradient contraction: w_ab = (beta_a alpha_hat_b - Khat^-1_ab) k_ab ; everything scaled at the end
-  float beta[NS], S1[NS][FT], S2[FT], Sk = 0.0f, Str = 0.0f;
-#pragma unroll
-  for (int f = 0; f < FT; ++f) S2[f] = 0.0f;
+  float beta[NS], S1[NS][FT], Sk = 0.0f, Str = 0.0f;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     beta[s] = aug[s] * inv_tot;
-    if (valid[s]) Str += fmaf(beta[s], aug[s], dg[s]) - 2.0f;
+    if (valid[s]) Str += fmaf(beta[s], aug[s], dg[s]);
 #pragma unroll
     for (int f = 0; f < FT; ++f) S1[s][f] = 0.0f;
   }
@@ -244,9 +325,9 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
     if (b < n) {
       float fb[RS];
 #pragma unroll
-      for (int c = 0; c < RS / 4; ++c) {
-        const float4 v = lds4(&sf[b][4 * c]);
-        fb[4 * c] = v.x; fb[4 * c + 1] = v.y; fb[4 * c + 2] = v.z; fb[4 * c + 3] = v.w;
+      for (int c4 = 0; c4 < RS / 4; ++c4) {
+        const float4 v = lds4(&sf[b][4 * c4]);
+        fb[4 * c4] = v.x; fb[4 * c4 + 1] = v.y; fb[4 * c4 + 2] = v.z; fb[4 * c4 + 3] = v.w;
       }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
@@ -256,38 +337,40 @@ __global__ void __launch_bounds__(kGpWarps * 32) gp_mll_kernel(GpArgs a) {
           du[f] = u[s][f] - fb[f];
           e = fmaf(-du[f], du[f], e);
         }
-        const float w = fmaf(beta[s], fb[FT], A[s][b]) * ex2_approx(e);
-        Sk += w;
+        const float wv = fmaf(beta[s], fb[FT], A[s][b]) * ex2_approx(e);
+        Sk += wv;
 #pragma unroll
-        for (int f = 0; f < FT; ++f) {
-          const float tdu = w * du[f];
-          S1[s][f] += tdu;
-          S2[f] = fmaf(tdu, du[f], S2[f]);
-        }
+        for (int f = 0; f < FT; ++f) S1[s][f] = fmaf(wv, du[f], S1[s][f]);
       }
     }
   }
 
   // ---- write-out.  G = g' / (2 tot);  W = rho/2 g' k;  all gradients are of mll = L / n.
+  //      sum_ab w_ab du_ab^2 = 2 sum_a u_a S1_a   (w symmetric, du antisymmetric) gives the lengthscale gradient.
+  float S2[FT];
+#pragma unroll
+  for (int f = 0; f < FT; ++f) S2[f] = 0.0f;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const int row = lane + 32 * s;
     if (row < n) {
       const size_t q = (size_t)p * Q + (size_t)t * n + row;
       if (a.dmean != nullptr) a.dmean[q] = beta[s] * inv_n;
-      if (a.dfeat != nullptr) {
 #pragma unroll
-        for (int f = 0; f < FT; ++f)
-          if (f < F) a.dfeat[q * F + f] = -rho * inv_n * inv_ls[f] / (kC * kC) * S1[s][f];
+      for (int f = 0; f < FT; ++f) {
+        if (f < F) {
+          // sum_a S1_a = 0, so any common offset may be removed from u_a: centre on row 0 against cancellation
+          S2[f] = fmaf(2.0f * (u[s][f] - sf[0][f]), S1[s][f], S2[f]);
+          if (a.dfeat != nullptr) a.dfeat[q * F + f] = -rho * inv_n * inv_ls[f] / (kC * kC) * S1[s][f];
+        }
       }
     }
   }
-  // rows beyond n contribute exact zeros to the sums (beta = 0, A row = 0)
   float dmean_sum = 0.0f;
 #pragma unroll
   for (int s = 0; s < NS; ++s) dmean_sum += beta[s];
   dmean_sum = warp_sum(dmean_sum) * inv_n;
-  Sk = warp_sum(Sk) - 2.0f * (float)n;     // remove the +2 diagonal offset (k_aa = 1)
+  Sk = warp_sum(Sk) - (float)n * (1.0f + rho);   // the diagonal registers carry +2 - dadd = 1 + rho  (k_aa = 1)
   Str = warp_sum(Str);
 #pragma unroll
   for (int f = 0; f < FT; ++f) S2[f] = warp_sum(S2[f]);

@@ -95,7 +95,7 @@ __device__ __forceinline__ void load_tile(float* sx, float* sdout, const MlpArgs
   int src = 0;
   if (valid) {
     int t = q / a.n;
-    src = __ldg(a.task_idx + t) * a.n + (q - t * a.n);
+    src = (a.task_idx != nullptr ? __ldg(a.task_idx + t) : t) * a.n + (q - t * a.n);
   }
 #pragma unroll
   for (int dd = 0; dd < DIN; ++dd) sx[dd * kTileP + lane] = (valid && dd < a.d) ? __ldg(a.x + (size_t)src * a.d + dd) : 0.0f;

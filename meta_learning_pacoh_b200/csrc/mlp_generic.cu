@@ -19,7 +19,7 @@ __device__ __forceinline__ int sum_widths(const NetDev& n) {
 
 __device__ __forceinline__ int gather_src(const MlpArgs& a, int q) {
   const int t = q / a.n;
-  return __ldg(a.task_idx + t) * a.n + (q - t * a.n);
+  return (a.task_idx != nullptr ? __ldg(a.task_idx + t) : t) * a.n + (q - t * a.n);
 }
 
 // acts[p][foff_l + j][q] = tanh(b_l[j] + sum_k W_l[j][k] acts[p][foff_{l-1} + k][q]);  out = Wout h_L + bout

@@ -206,6 +206,16 @@ def logprob_finalize(theta, prior_mu, prior_sigma, prior_factor, pre, packed, wa
     return logp, dtheta
 
 
+def meta_log_prob_and_score(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None):
+    """(logp (P,), score = d logp / d theta (P, D), info) without autograd: what SVGD.phi needs (svgd.py:13-16).
+    ``task_idx`` is this rank's shard when ``group`` is given; ``pre`` is computed from the GLOBAL batch."""
+    _, packed, info = engine.mll_fwd_bwd(theta, task_idx, want_mll=False, want_info=True)
+    if group is not None:
+        torch.distributed.all_reduce(packed, group=group)
+    logp, dtheta = logprob_finalize(theta, prior_mu, prior_sigma, prior_factor, pre, packed)
+    return logp, dtheta, info
+
+
 class MetaLogProb(torch.autograd.Function):
     """logp_p = prior_factor * log p(theta_p) + pre_factor * sum_t mll_{p,t} with its analytic gradient.
 
@@ -217,11 +227,8 @@ class MetaLogProb(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None):
-        th = theta.detach().contiguous()
-        _, packed, info = engine.mll_fwd_bwd(th, task_idx, want_mll=False, want_info=True)
-        if group is not None:
-            torch.distributed.all_reduce(packed, group=group)
-        logp, dtheta = logprob_finalize(th, prior_mu, prior_sigma, prior_factor, pre, packed)
+        logp, dtheta, info = meta_log_prob_and_score(theta.detach().contiguous(), engine, task_idx, prior_mu, prior_sigma,
+                                                     prior_factor, pre, group)
         ctx.save_for_backward(dtheta)
         ctx.info = info
         ctx.mark_non_differentiable(info)
@@ -288,3 +295,118 @@ def ffma_peak_tflops(iters=4096, reps=5):
         e1.synchronize()
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+def gp_forward(arch: GPArch, theta, x):
+    """mean (P, npts) and features (P, npts, F) of the learned nets at x (npts, d): pacoh_gp_forward.
+    For constant / zero mean and the plain SE kernel the trivial values are filled in here."""
+    theta, x = theta.contiguous(), x.contiguous()
+    P, npts = theta.shape[0], x.shape[0]
+    dev = theta.device
+    a = arch.c_struct()
+    nbytes = check(lib.pacoh_gp_forward_workspace_bytes(ctypes.byref(a), P, npts))
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    mean = torch.empty(P, npts, dtype=torch.float32, device=dev) if arch.mean_kind == "NN" else None
+    feat = torch.empty(P, npts, arch.feature_dim, dtype=torch.float32, device=dev) if arch.covar_kind == "NN" else None
+    check(lib.pacoh_gp_forward(ctypes.byref(a), P, npts, _ptr(theta), _ptr(x), _ptr(mean), _ptr(feat), _ptr(ws), ws.numel(), _stream()))
+    ent = arch.entries()
+    if mean is None:
+        if arch.mean_kind == "constant":
+            c0 = ent["constant_mean"][0]
+            mean = theta[:, c0:c0 + 1].expand(P, npts).contiguous()
+        else:
+            mean = torch.zeros(P, npts, dtype=torch.float32, device=dev)
+    if feat is None:
+        feat = x.unsqueeze(0).expand(P, npts, x.shape[1]).contiguous()
+    return mean, feat
+
+
+def gp_hypers(arch: GPArch, theta):
+    """lengthscale (P, F), noise variance (P,), outputscale (P,) from the raw entries (random_gp.py:69-73)."""
+    ent = arch.entries()
+    sp = torch.nn.functional.softplus
+    a, b = ent["lengthscale_raw"]
+    ls = sp(theta[:, a:b])
+    noise = sp(theta[:, ent["noise_raw"][0]]) + arch.noise_floor
+    osc = sp(theta[:, ent["outputscale_raw"][0]]) if arch.outputscale else torch.ones_like(noise)
+    return ls, noise, osc
+
+
+def gp_posterior(arch: GPArch, theta, x_context, y_context, x_test):
+    """Eval-mode exact GP posterior for every parameter vector (gpytorch ExactGP.eval + likelihood, reached from
+    get_pred_dist, GPR_meta_svgd.py:203-212 / GPR_meta_vi.py:229-252 / GPR_meta_mll.py:174-183):
+        mu* = m(X*) + K*^T Kt^-1 (y - m(X)),  Sigma* = K** - K*^T Kt^-1 K* + sigma^2 I     (normalised space)
+    The nets run in the CUDA kernels (pacoh_gp_forward); the n_c x n_c / n* x n* dense algebra uses torch.linalg on
+    the device -- SURVEY 8(f).1 ranks a dedicated posterior kernel as the next row.
+    Returns mean (P, n*), covariance (P, n*, n*) including observation noise."""
+    nc = x_context.shape[0]
+    xa = torch.cat([x_context, x_test], 0)
+    mean, feat = gp_forward(arch, theta, xa)
+    ls, noise, osc = gp_hypers(arch, theta)
+    u = feat / ls.unsqueeze(1)
+    uc, us = u[:, :nc], u[:, nc:]
+
+    def gram(a, b):
+        d2 = (a.unsqueeze(2) - b.unsqueeze(1)).pow(2).sum(-1)
+        return osc.view(-1, 1, 1) * torch.exp(-0.5 * d2)
+
+    P = theta.shape[0]
+    eye_c = torch.eye(nc, device=theta.device, dtype=torch.float32)
+    eye_s = torch.eye(x_test.shape[0], device=theta.device, dtype=torch.float32)
+    Kcc = gram(uc, uc) + noise.view(P, 1, 1) * eye_c
+    Kcs, Kss = gram(uc, us), gram(us, us)
+    L, info = torch.linalg.cholesky_ex(Kcc)
+    if int(info.max().item()) > 0:
+        raise NotPSDError("context kernel matrix is not positive definite")
+    r = (y_context.view(1, nc) - mean[:, :nc]).unsqueeze(-1)
+    alpha = torch.cholesky_solve(r, L)
+    mu = mean[:, nc:] + (Kcs.transpose(1, 2) @ alpha).squeeze(-1)
+    V = torch.linalg.solve_triangular(L, Kcs, upper=False)
+    cov = Kss - V.transpose(1, 2) @ V + noise.view(P, 1, 1) * eye_s
+    return mu, cov
+
+
+class PacohAdam(torch.optim.Optimizer):
+    """torch.optim.Adam-compatible optimizer (same state keys: step / exp_avg / exp_avg_sq, same update order) whose
+    step is one fused CUDA kernel over the flat (P, D) particle matrix (pacoh_adam_step).  ``direction`` lets the
+    SVGD step feed phi directly (grad = -phi, svgd.py:27) without materialising ``.grad``."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, direction=None):
+        for group in self.param_groups:
+            for p in group["params"]:
+                g, sign = (direction, -1.0) if direction is not None else (p.grad, 1.0)
+                if g is None:
+                    continue
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                b1, b2 = group["betas"]
+                assert p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32
+                check(lib.pacoh_adam_step(p.numel(), _ptr(p), _ptr(g), sign, _ptr(st["exp_avg"]), _ptr(st["exp_avg_sq"]),
+                                          float(group["lr"]), float(b1), float(b2), float(group["eps"]), int(st["step"]), _stream()))
+
+
+class StageTiming:
+    """Context manager around pacoh_stage_timing_*: per-stage device milliseconds of pacoh_meta_mll_fwd_bwd."""
+    NAMES = ("mlp_fwd", "gp_mll", "mlp_bwd", "reduce")
+
+    def __enter__(self):
+        check(lib.pacoh_stage_timing_enable(1))
+        return self
+
+    def read(self):
+        ms = (ctypes.c_float * 4)()
+        calls = ctypes.c_int32(0)
+        check(lib.pacoh_stage_timing_read(ms, ctypes.byref(calls)))
+        return {n: float(ms[i]) for i, n in enumerate(self.NAMES)}, int(calls.value)
+
+    def __exit__(self, *exc):
+        check(lib.pacoh_stage_timing_enable(0))
+        return False

@@ -1,0 +1,248 @@
+"""PACOH-MAP on the B200 engine: call-compatible with the reference's meta_learn/GPR_meta_mll.py:12-264
+(GPRegressionMetaLearned).  The parameters stay ordinary torch modules (same names and state_dict keys as the
+reference's LearnedGPRegressionModel, so checkpoints interchange); every iteration packs them into the engine's flat
+layout, evaluates loss = -sum_{t in batch} mll_t and its gradient with ONE pacoh_meta_mll_fwd_bwd call (P = 1,
+ScaleKernel outputscale, noise floor 1e-3) instead of the per-task loop (GPR_meta_mll.py:109-113), and scatters the
+gradient back into ``.grad`` for torch's AdamW / SGD.
+"""
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import engine as eng
+from .abstract import RegressionModelMetaLearned
+from .distributions import AffineTransformedDistribution
+from .util import DummyLRScheduler, _handle_input_dimensionality
+
+
+class NeuralNetwork(torch.nn.Sequential):
+    """tanh MLP with submodules fc_1..fc_L, out (same names / init order as meta_learn/models.py:190-217)."""
+
+    def __init__(self, input_dim=2, output_dim=2, layer_sizes=(64, 64)):
+        super().__init__()
+        self.n_layers = len(layer_sizes)
+        prev = input_dim
+        for i, size in enumerate(layer_sizes):
+            setattr(self, 'fc_%i' % (i + 1), torch.nn.Linear(prev, size))
+            prev = size
+        setattr(self, 'out', torch.nn.Linear(prev, output_dim))
+
+    def linears(self):
+        return [getattr(self, 'fc_%i' % i) for i in range(1, self.n_layers + 1)] + [self.out]
+
+    def forward(self, x):
+        for lin in self.linears()[:-1]:
+            x = torch.tanh(lin(x))
+        return self.out(x)
+
+
+class GPRegressionMetaLearned(RegressionModelMetaLearned):
+
+    def __init__(self, meta_train_data, learning_mode='both', lr_params=1e-3, weight_decay=0.0, feature_dim=2,
+                 num_iter_fit=10000, covar_module='NN', mean_module='NN', mean_nn_layers=(32, 32), kernel_nn_layers=(32, 32),
+                 task_batch_size=5, normalize_data=True, optimizer='Adam', lr_decay=1.0, random_seed=None):
+        """Meta-learning GP priors (mean and kernel function) via PACOH-MAP.  Args identical to the reference
+        (GPR_meta_mll.py:14-37); gpytorch Kernel/Mean objects as covar_module / mean_module are not supported."""
+        super().__init__(normalize_data, random_seed)
+        assert learning_mode in ['learn_mean', 'learn_kernel', 'both', 'vanilla']
+        assert mean_module in ['NN', 'constant', 'zero'], "gpytorch Mean objects are outside the CUDA path"
+        assert covar_module in ['NN', 'SE'], "gpytorch Kernel objects are outside the CUDA path"
+        assert optimizer in ['Adam', 'SGD']
+
+        self.lr_params, self.weight_decay, self.feature_dim = lr_params, weight_decay, feature_dim
+        self.num_iter_fit, self.task_batch_size, self.normalize_data = num_iter_fit, task_batch_size, normalize_data
+        self.learning_mode = learning_mode
+
+        self._check_meta_data_shapes(meta_train_data)
+        self._compute_normalization_stats(meta_train_data)
+        self._setup_gp_prior(mean_module, covar_module, learning_mode, feature_dim, mean_nn_layers, kernel_nn_layers)
+
+        # likelihood: noise = 1e-3 + softplus(raw_noise), raw_noise (1,) = 0  (GPR_meta_mll.py:54-56)
+        self.raw_noise = torch.nn.Parameter(torch.zeros(1, device=self.device))
+        self.shared_parameters.append({'params': [self.raw_noise], 'lr': self.lr_params})
+
+        X, Y = self._build_task_dicts(meta_train_data)
+        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
+        self._setup_optimizer(optimizer, lr_params, lr_decay)
+        self.fitted = False
+
+    # ------------------------------------------------------------------ flat-layout packing
+    def _named_flat(self):
+        """[(flat-layout name, tensor)] in the engine's order."""
+        out = []
+        for prefix, net in (("mean_nn", self.nn_mean_fn), ("kernel_nn", self.nn_kernel_map)):
+            if net is None:
+                continue
+            lins = net.linears()
+            names = ["fc_%d" % (i + 1) for i in range(len(lins) - 1)] + ["out"]
+            for nm, lin in zip(names, lins):
+                out.append(("%s.%s.bias" % (prefix, nm), lin.bias))
+                out.append(("%s.%s.weight" % (prefix, nm), lin.weight))
+        if self.arch.mean_kind == "constant":
+            out.insert(0, ("constant_mean", self.constant_mean))
+        out.append(("lengthscale_raw", self.raw_lengthscale))
+        out.append(("noise_raw", self.raw_noise))
+        out.append(("outputscale_raw", self.raw_outputscale))
+        assert [n for n, _ in out] == list(self.arch.entries().keys())
+        return out
+
+    def _pack(self):
+        return torch.cat([t.detach().reshape(-1) for _, t in self._named_flat()]).view(1, -1).contiguous()
+
+    def _scatter_grad(self, flat_grad):
+        learn_kernel = self.learning_mode in ("learn_kernel", "both")
+        learn_mean = self.learning_mode in ("learn_mean", "both")
+        for (name, t), (a, b) in zip(self._named_flat(), self.arch.entries().values()):
+            trainable = {"mean_nn": learn_mean, "constant_mean": learn_mean, "kernel_nn": learn_kernel,
+                         "lengthscale_raw": learn_kernel, "outputscale_raw": learn_kernel, "noise_raw": True}[name.split(".")[0]]
+            if trainable:
+                t.grad = flat_grad[a:b].view_as(t).clone()
+
+    # ------------------------------------------------------------------ training
+    def meta_fit(self, valid_tuples=None, verbose=True, log_period=500, n_iter=None):
+        """Meta-learns the GP prior parameters -- GPR_meta_mll.py:82-147."""
+        assert (valid_tuples is None) or (all([len(valid_tuple) == 4 for valid_tuple in valid_tuples]))
+        loss = torch.zeros((), device=self.device)
+        if self.learning_mode != 'vanilla':
+            t = time.time()
+            cum_loss = torch.zeros((), device=self.device)
+            if n_iter is None:
+                n_iter = self.num_iter_fit
+            for itr in range(1, n_iter + 1):
+                self.optimizer.zero_grad()
+                task_idx = self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size)
+                loss = self._loss_and_grad(task_idx)
+                self.optimizer.step()
+                self.lr_scheduler.step()
+                cum_loss = cum_loss + loss
+                if itr == 1 or itr % log_period == 0:
+                    eng.check_info(self._last_info)
+                    duration = time.time() - t
+                    avg_loss = cum_loss / (log_period if itr > 1 else 1.0)
+                    cum_loss = torch.zeros((), device=self.device)
+                    t = time.time()
+                    message = 'Iter %d/%d - Loss: %.6f - Time %.2f sec' % (itr, self.num_iter_fit, avg_loss.item(), duration)
+                    if valid_tuples is not None:
+                        valid_ll, valid_rmse, calibr_err = self.eval_datasets(valid_tuples)
+                        message += ' - Valid-LL: %.3f - Valid-RMSE: %.3f - Calib-Err %.3f' % (valid_ll, valid_rmse, calibr_err)
+                    if verbose:
+                        self.logger.info(message)
+        else:
+            self.logger.info('Vanilla mode - nothing to fit')
+        self.fitted = True
+        return loss.item()
+
+    def _loss_and_grad(self, task_idx):
+        idx = torch.as_tensor(np.asarray(task_idx, dtype=np.int32)).to(self.device)
+        theta = self._pack()
+        _, packed, info = self.engine.mll_fwd_bwd(theta, idx, want_mll=False, want_info=True)
+        D = self.arch.D
+        self._scatter_grad(-packed[:D])                 # loss = - sum_t mll_t
+        self._last_info = info
+        return -packed[D]
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, context_x, context_y, test_x, return_density=False):
+        """Posterior inference on the context set, predictive distribution at test_x -- GPR_meta_mll.py:149-190."""
+        mu, cov = self._predict_normalised(context_x, context_y, test_x)
+        base = torch.distributions.MultivariateNormal(mu[0].cpu(), covariance_matrix=cov[0].cpu())
+        pred = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
+        if return_density:
+            return pred
+        return pred.mean.numpy(), pred.stddev.numpy()
+
+    def _predict_normalised(self, context_x, context_y, test_x):
+        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
+        test_x = _handle_input_dimensionality(test_x)
+        assert test_x.shape[1] == context_x.shape[1]
+        xc, yc = self._prepare_data_per_task(context_x, context_y)
+        xs = torch.from_numpy(self._normalize_data(X=test_x, Y=None)).float().to(self.device)
+        with torch.no_grad():
+            return eng.gp_posterior(self.arch, self._pack(), xc, yc, xs)
+
+    # ------------------------------------------------------------------ checkpointing (GPR_meta_mll.py:192-205)
+    def _model_state(self):
+        sd = OrderedDict()
+        sd['likelihood.noise_covar.raw_noise'] = self.raw_noise.detach().clone()
+        if self.arch.mean_kind == "constant":
+            sd['mean_module.constant'] = self.constant_mean.detach().clone()
+        sd['covar_module.raw_outputscale'] = self.raw_outputscale.detach().clone()
+        sd['covar_module.base_kernel.raw_lengthscale'] = self.raw_lengthscale.detach().clone()
+        for prefix, net in (('learned_kernel', self.nn_kernel_map), ('learned_mean', self.nn_mean_fn)):
+            if net is not None:
+                for k, v in net.state_dict().items():
+                    sd['%s.%s' % (prefix, k)] = v.detach().clone()
+        return sd
+
+    def state_dict(self):
+        # deep copy: torch >= 2 no longer copies optimizer state tensors in load_state_dict, so a snapshot that aliases
+        # the live exp_avg buffers would be shared between two learners
+        import copy
+        return {'optimizer': copy.deepcopy(self.optimizer.state_dict()), 'model': self._model_state()}
+
+    def load_state_dict(self, state_dict):
+        sd = state_dict['model']
+        with torch.no_grad():
+            self.raw_noise.copy_(sd['likelihood.noise_covar.raw_noise'])
+            if self.arch.mean_kind == "constant":
+                self.constant_mean.copy_(sd['mean_module.constant'])
+            self.raw_outputscale.copy_(sd['covar_module.raw_outputscale'])
+            self.raw_lengthscale.copy_(sd['covar_module.base_kernel.raw_lengthscale'])
+        for prefix, net in (('learned_kernel', self.nn_kernel_map), ('learned_mean', self.nn_mean_fn)):
+            if net is not None:
+                net.load_state_dict({k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + '.')})
+        self.optimizer.load_state_dict(state_dict['optimizer'])
+
+    # ------------------------------------------------------------------ setup
+    def _setup_gp_prior(self, mean_module, covar_module, learning_mode, feature_dim, mean_nn_layers, kernel_nn_layers):
+        """Module construction order = RNG consumption order of the reference (GPR_meta_mll.py:207-251): kernel net
+        first, then mean net; raw lengthscale (1, F), raw outputscale (), constant mean start at 0."""
+        self.shared_parameters = []
+        if covar_module == 'NN':
+            assert learning_mode in ['learn_kernel', 'both'], 'neural network parameters must be learned'
+            self.nn_kernel_map = NeuralNetwork(input_dim=self.input_dim, output_dim=feature_dim,
+                                               layer_sizes=kernel_nn_layers).to(self.device)
+            self.shared_parameters.append({'params': self.nn_kernel_map.parameters(), 'lr': self.lr_params,
+                                           'weight_decay': self.weight_decay})
+            n_feat = feature_dim
+        else:
+            self.nn_kernel_map = None
+            n_feat = self.input_dim
+        if mean_module == 'NN':
+            assert learning_mode in ['learn_mean', 'both'], 'neural network parameters must be learned'
+            self.nn_mean_fn = NeuralNetwork(input_dim=self.input_dim, output_dim=1, layer_sizes=mean_nn_layers).to(self.device)
+            self.shared_parameters.append({'params': self.nn_mean_fn.parameters(), 'lr': self.lr_params,
+                                           'weight_decay': self.weight_decay})
+        else:
+            self.nn_mean_fn = None
+        self.raw_lengthscale = torch.nn.Parameter(torch.zeros(1, n_feat, device=self.device))
+        self.raw_outputscale = torch.nn.Parameter(torch.zeros((), device=self.device))
+        if mean_module == 'constant':
+            self.constant_mean = torch.nn.Parameter(torch.zeros(1, device=self.device))
+        if learning_mode in ["learn_kernel", "both"]:
+            self.shared_parameters.append({'params': [self.raw_lengthscale, self.raw_outputscale], 'lr': self.lr_params})
+        if learning_mode in ["learn_mean", "both"] and mean_module == 'constant':
+            self.shared_parameters.append({'params': [self.constant_mean], 'lr': self.lr_params})
+        self.arch = eng.GPArch(self.input_dim, mean_kind=mean_module, covar_kind=covar_module,
+                               mean_layers=tuple(mean_nn_layers), kernel_layers=tuple(kernel_nn_layers),
+                               feature_dim=feature_dim, outputscale=True, noise_floor=1e-3)
+        self._last_info = None
+
+    def _setup_optimizer(self, optimizer, lr, lr_decay):
+        # AdamW's constructor-level weight_decay also applies to the groups that did not set one (likelihood, covar,
+        # mean hypers) -- a reference quirk pinned by the demo.ipynb trajectory (GPR_meta_mll.py:56, 248-255)
+        if optimizer == 'Adam':
+            self.optimizer = torch.optim.AdamW(self.shared_parameters, lr=lr, weight_decay=self.weight_decay)
+        elif optimizer == 'SGD':
+            self.optimizer = torch.optim.SGD(self.shared_parameters, lr=lr)
+        else:
+            raise NotImplementedError('Optimizer must be Adam or SGD')
+        if lr_decay < 1.0:
+            self.lr_scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, 1000, gamma=lr_decay)
+        else:
+            self.lr_scheduler = DummyLRScheduler()
+
+    def _vectorize_pred_dist(self, pred_dist):
+        return torch.distributions.Normal(pred_dist.mean, pred_dist.stddev)

@@ -1,0 +1,202 @@
+"""PACOH-SVGD on the B200 engine: same constructor, attributes and methods as the reference's
+meta_learn/GPR_meta_svgd.py:14-235 (GPRegressionMetaLearnedSVGD), with the per-task / per-particle Python loops
+(random_gp.py:214-217, svgd.py:12-28) replaced by three C-ABI calls per step:
+
+    pacoh_meta_mll_fwd_bwd  ->  [NCCL all-reduce when task-sharded]  ->  pacoh_logprob_finalize
+    pacoh_svgd_phi          ->  pacoh_adam_step
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import engine as eng
+from . import prior_init
+from .abstract import RegressionModelMetaLearned
+from .distributions import AffineTransformedDistribution, EqualWeightedMixtureDist
+from .util import DummyLRScheduler, _handle_input_dimensionality
+
+
+class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
+
+    def __init__(self, meta_train_data, num_iter_fit=10000, feature_dim=1,
+                 prior_factor=0.01, weight_prior_std=0.5, bias_prior_std=3.0,
+                 covar_module='NN', mean_module='NN', mean_nn_layers=(32, 32), kernel_nn_layers=(32, 32),
+                 optimizer='Adam', lr=1e-3, lr_decay=1.0, kernel='RBF', bandwidth=None, num_particles=10,
+                 task_batch_size=-1, normalize_data=True, random_seed=None):
+        """PACOH-SVGD: Stein variational gradient descent on the PAC-optimal hyper-posterior over GP priors.
+
+        Args: identical to the reference (GPR_meta_svgd.py:16-45).  ``feature_dim`` is accepted and ignored exactly
+        as the reference does (its kernel net always has 2 outputs: GPR_meta_svgd.py:167-170, random_gp.py:24).
+        """
+        super().__init__(normalize_data, random_seed)
+        assert mean_module in ['NN', 'constant', 'zero']
+        assert covar_module in ['NN', 'SE']
+        assert optimizer in ['Adam', 'SGD']
+
+        self.num_iter_fit, self.prior_factor, self.feature_dim = num_iter_fit, prior_factor, feature_dim
+        self.weight_prior_std, self.bias_prior_std = weight_prior_std, bias_prior_std
+        self.num_particles = num_particles
+        if task_batch_size < 1:
+            self.task_batch_size = len(meta_train_data)
+        else:
+            self.task_batch_size = min(task_batch_size, len(meta_train_data))
+
+        self._check_meta_data_shapes(meta_train_data)
+        self._compute_normalization_stats(meta_train_data)
+
+        self._setup_model_inference(mean_module, covar_module, mean_nn_layers, kernel_nn_layers,
+                                    kernel, bandwidth, optimizer, lr, lr_decay)
+
+        X, Y = self._build_task_dicts(meta_train_data)
+        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
+        self._idx_host = torch.empty(self.task_batch_size, dtype=torch.int32).pin_memory()
+        self._group = None
+        self._rank, self._world = 0, 1
+        self.fitted = False
+
+    # ------------------------------------------------------------------ multi-GPU
+    def shard_tasks(self, group=None):
+        """Task-shard the sampled batch over the ranks of ``group`` (default: the world group).  Every rank must be
+        constructed with the same data and seed: all ranks then draw the same batch indices, evaluate a contiguous
+        slice of them, and one NCCL all-reduce of the packed (P, D+1) likelihood buffer restores the full sums."""
+        import torch.distributed as dist
+        assert dist.is_initialized()
+        self._group = group if group is not None else dist.group.WORLD
+        self._rank, self._world = dist.get_rank(self._group), dist.get_world_size(self._group)
+        return self
+
+    # ------------------------------------------------------------------ training
+    def meta_fit(self, valid_tuples=None, verbose=True, log_period=500, n_iter=None):
+        """Fits the hyper-posterior particles with SVGD -- GPR_meta_svgd.py:82-121."""
+        assert (valid_tuples is None) or (all([len(valid_tuple) == 4 for valid_tuple in valid_tuples]))
+        t = time.time()
+        if n_iter is None:
+            n_iter = self.num_iter_fit
+        for itr in range(1, n_iter + 1):
+            task_idx = self._sample_task_indices()
+            self.svgd_step(task_idx)
+            self.lr_scheduler.step()
+            if itr == 1 or itr % log_period == 0:
+                eng.check_info(self._last_info)
+                duration = time.time() - t
+                t = time.time()
+                message = 'Iter %d/%d - Time %.2f sec' % (itr, self.num_iter_fit, duration)
+                if valid_tuples is not None:
+                    valid_ll, valid_rmse, calibr_err = self.eval_datasets(valid_tuples)
+                    message += ' - Valid-LL: %.3f - Valid-RMSE: %.3f - Calib-Err %.3f' % (valid_ll, valid_rmse, calibr_err)
+                if verbose:
+                    self.logger.info(message)
+        self.fitted = True
+
+    def svgd_step(self, task_idx):
+        """One SVGD update on the sampled batch (closure svgd_step, GPR_meta_svgd.py:190-199 -> svgd.py:25-28).
+        ``task_idx``: numpy / sequence of task indices into the meta-training set (with repetitions)."""
+        idx = np.asarray(task_idx, dtype=np.int32)
+        T = idx.shape[0]
+        lo, hi = (self._rank * T) // self._world, ((self._rank + 1) * T) // self._world
+        if self._idx_host.numel() < hi - lo:
+            self._idx_host = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
+        self._idx_host[:hi - lo].copy_(torch.from_numpy(idx[lo:hi]))
+        idx_dev = self._idx_host[:hi - lo].to(self.device, non_blocking=True)
+        pre = eng.pre_factor([self.engine.n] * T)                      # GLOBAL batch (random_gp.py:209-212)
+        logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
+                                                        self._prior_sigma, self.prior_factor, pre, self._group)
+        phi = self._phi(self.particles, score)
+        if isinstance(self.optimizer, eng.PacohAdam):
+            self.optimizer.step(direction=phi)                         # grad = -phi (svgd.py:27)
+        else:
+            self.optimizer.zero_grad()
+            self.particles.grad = -phi
+            self.optimizer.step()
+        self._last_info, self._last_logp = info, logp
+        return logp
+
+    def svgd_step_host(self, x_batch, y_batch):
+        """Same update as svgd_step, fed like the reference's closure is (GPR_meta_svgd.py:190-199 receives the sampled
+        task tensors themselves): ``x_batch`` (T, n, d) / ``y_batch`` (T, n) are HOST tensors (pinned for async copies)
+        holding the sampled, normalised batch in order.  They are copied to the device, the step runs on them with
+        identity task indices, and logp (P,) is returned on the host.  Used for the end-to-end measurement."""
+        T = x_batch.shape[0]
+        lo, hi = (self._rank * T) // self._world, ((self._rank + 1) * T) // self._world
+        if getattr(self, "_stage_engine", None) is None or self._stage_engine.T_total != hi - lo:
+            xs = torch.empty((hi - lo,) + tuple(x_batch.shape[1:]), dtype=torch.float32)
+            ys = torch.empty((hi - lo,) + tuple(y_batch.shape[1:]), dtype=torch.float32)
+            self._stage_engine = eng.MetaMLLEngine(self.arch, xs, ys, self.device)
+            self._stage_idx = torch.arange(hi - lo, dtype=torch.int32, device=self.device)
+        se = self._stage_engine
+        se.x.copy_(x_batch[lo:hi], non_blocking=True)
+        se.y.copy_(y_batch[lo:hi], non_blocking=True)
+        pre = eng.pre_factor([se.n] * T)
+        logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx, self._prior_mu,
+                                                        self._prior_sigma, self.prior_factor, pre, self._group)
+        phi = self._phi(self.particles, score)
+        if isinstance(self.optimizer, eng.PacohAdam):
+            self.optimizer.step(direction=phi)
+        else:
+            self.optimizer.zero_grad()
+            self.particles.grad = -phi
+            self.optimizer.step()
+        self._last_info = info
+        return logp.cpu()
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, context_x, context_y, test_x, return_density=False):
+        """Posterior inference on (context_x, context_y), predictive mixture over particles at test_x --
+        GPR_meta_svgd.py:123-159."""
+        mu, cov = self._predict_normalised(context_x, context_y, test_x)
+        base = torch.distributions.MultivariateNormal(mu.cpu(), covariance_matrix=cov.cpu())
+        pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
+        pred_dist = EqualWeightedMixtureDist(pred_dist, batched=True)
+        if return_density:
+            return pred_dist
+        return pred_dist.mean.numpy(), pred_dist.stddev.numpy()
+
+    def _predict_normalised(self, context_x, context_y, test_x):
+        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
+        test_x = _handle_input_dimensionality(test_x)
+        assert test_x.shape[1] == context_x.shape[1]
+        xc, yc = self._prepare_data_per_task(context_x, context_y)
+        xs = torch.from_numpy(self._normalize_data(X=test_x, Y=None)).float().to(self.device)
+        with torch.no_grad():
+            return eng.gp_posterior(self.arch, self.particles, xc, yc, xs)
+
+    # ------------------------------------------------------------------ setup
+    def _setup_model_inference(self, mean_module_str, covar_module_str, mean_nn_layers, kernel_nn_layers,
+                               kernel, bandwidth, optimizer, lr, lr_decay):
+        assert mean_module_str in ['NN', 'constant']
+        assert covar_module_str in ['NN', 'SE']
+        # random GP model: RandomGPMeta(size_in, prior_factor, ..., covar_module_str, mean_module_str, layers)
+        # (GPR_meta_svgd.py:166-170); feature_dim is NOT forwarded there -> always 2 (random_gp.py:24)
+        self.arch = eng.GPArch(self.input_dim, mean_kind=mean_module_str, covar_kind=covar_module_str,
+                               mean_layers=tuple(mean_nn_layers), kernel_layers=tuple(kernel_nn_layers), feature_dim=2)
+        prior_init.consume_vectorized_gp_init(self.arch)
+        mu, sigma = self.arch.hyper_prior(self.weight_prior_std, self.bias_prior_std)
+        self._prior_mu, self._prior_sigma = mu.to(self.device), sigma.to(self.device)
+
+        if kernel not in ('RBF', 'IMQ'):
+            raise NotImplementedError
+        # initial particle locations from the hyper-prior (GPR_meta_svgd.py:182)
+        self.particles = prior_init.sample_params_from_prior(self.arch, self.num_particles, self.weight_prior_std,
+                                                             self.bias_prior_std).contiguous().to(self.device)
+        self._phi = eng.SVGDDirection(self.num_particles, self.arch.D, self.device, bandwidth=bandwidth, kernel=kernel)
+        self._setup_optimizer(optimizer, lr, lr_decay)
+        self._last_info = None
+
+    def _setup_optimizer(self, optimizer, lr, lr_decay):
+        assert hasattr(self, 'particles'), "SVGD must be initialized before setting up optimizer"
+        if optimizer == 'Adam':
+            self.optimizer = eng.PacohAdam([self.particles], lr=lr)
+        elif optimizer == 'SGD':
+            self.optimizer = torch.optim.SGD([self.particles], lr=lr)
+        else:
+            raise NotImplementedError('Optimizer must be Adam or SGD')
+        if lr_decay < 1.0:
+            self.lr_scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, 1000, gamma=lr_decay)
+        else:
+            self.lr_scheduler = DummyLRScheduler()
+
+    def _vectorize_pred_dist(self, pred_dist):
+        mvn = pred_dist.dists
+        normal = torch.distributions.Normal(mvn.mean, mvn.stddev)
+        return EqualWeightedMixtureDist(normal, batched=True, num_dists=mvn.batch_shape[0])

@@ -1,0 +1,239 @@
+"""PACOH-VI on the B200 engine: call-compatible with the reference's meta_learn/GPR_meta_vi.py:14-275
+(GPRegressionMetaLearnedVI).  Per step (get_neg_elbo, GPR_meta_vi.py:216-224):
+
+    eps ~ N(0, I) (S, D)  ->  pacoh_vi_sample  ->  pacoh_meta_mll_fwd_bwd / pacoh_logprob_finalize  ->  pacoh_vi_grad
+    ->  Adam on (loc, scale)
+
+``cov_type='full'`` keeps the D x D Cholesky factor in torch (autograd through the MetaLogProb Function), as the
+boundary table in SURVEY 8(b) specifies.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from .. import engine as eng
+from . import prior_init
+from .abstract import RegressionModelMetaLearned
+from .distributions import AffineTransformedDistribution, EqualWeightedMixtureDist
+from .util import DummyLRScheduler, _handle_input_dimensionality
+
+
+class _DiagPosterior(torch.nn.Module):
+    """Gaussian VI posterior on the GP-prior parameters (RandomGPPosterior, random_gp.py:224-286), diagonal case:
+    ``scale`` holds the LOG standard deviation."""
+
+    def __init__(self, loc, scale, entries):
+        super().__init__()
+        self.loc = torch.nn.Parameter(loc)
+        self.scale = torch.nn.Parameter(scale)
+        self.param_idx_ranges = entries
+
+    @property
+    def mean(self):
+        return self.loc.detach()
+
+    mode = mean
+
+    @property
+    def stddev(self):
+        return self.scale.detach().exp()
+
+
+class _FullPosterior(torch.nn.Module):
+    def __init__(self, loc, tril_cov, entries):
+        super().__init__()
+        self.loc = torch.nn.Parameter(loc)
+        self.tril_cov = torch.nn.Parameter(tril_cov)
+        self.param_idx_ranges = entries
+
+    def dist(self):
+        return torch.distributions.MultivariateNormal(loc=self.loc, scale_tril=torch.tril(self.tril_cov))
+
+    @property
+    def mean(self):
+        return self.loc.detach()
+
+    mode = mean
+
+    @property
+    def stddev(self):
+        return self.dist().stddev.detach()
+
+
+class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
+
+    def __init__(self, meta_train_data, num_iter_fit=10000, feature_dim=1,
+                 prior_factor=0.01, weight_prior_std=0.5, bias_prior_std=3.0,
+                 covar_module='NN', mean_module='NN', mean_nn_layers=(32, 32), kernel_nn_layers=(32, 32),
+                 optimizer='Adam', lr=1e-3, lr_decay=1.0, svi_batch_size=10, cov_type='diag',
+                 task_batch_size=-1, normalize_data=True, random_seed=None):
+        """PACOH-VI: variational inference on the PAC-optimal hyper-posterior with a Gaussian family.
+        Args identical to the reference (GPR_meta_vi.py:16-46)."""
+        super().__init__(normalize_data, random_seed)
+        assert mean_module in ['NN', 'constant', 'zero']
+        assert covar_module in ['NN', 'SE']
+        assert optimizer in ['Adam', 'SGD']
+        assert cov_type in ['diag', 'full']
+
+        self.num_iter_fit, self.prior_factor, self.feature_dim = num_iter_fit, prior_factor, feature_dim
+        self.weight_prior_std, self.bias_prior_std = weight_prior_std, bias_prior_std
+        self.svi_batch_size = svi_batch_size
+        self.cov_type = cov_type
+        if task_batch_size < 1:
+            self.task_batch_size = len(meta_train_data)
+        else:
+            self.task_batch_size = min(task_batch_size, len(meta_train_data))
+
+        self._check_meta_data_shapes(meta_train_data)
+        self._compute_normalization_stats(meta_train_data)
+        self._setup_model_inference(mean_module, covar_module, mean_nn_layers, kernel_nn_layers, cov_type)
+        self._setup_optimizer(optimizer, lr, lr_decay)
+
+        X, Y = self._build_task_dicts(meta_train_data)
+        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
+        self._group, self._rank, self._world = None, 0, 1
+        self._last_info = None
+        self.fitted = False
+
+    def shard_tasks(self, group=None):
+        """Task-shard the sampled batch over ranks (see GPRegressionMetaLearnedSVGD.shard_tasks)."""
+        import torch.distributed as dist
+        assert dist.is_initialized()
+        self._group = group if group is not None else dist.group.WORLD
+        self._rank, self._world = dist.get_rank(self._group), dist.get_world_size(self._group)
+        return self
+
+    # ------------------------------------------------------------------ training
+    def meta_fit(self, valid_tuples=None, verbose=True, log_period=500, n_iter=None):
+        """Fits the variational hyper-posterior by minimising the negative ELBO -- GPR_meta_vi.py:84-128."""
+        assert (valid_tuples is None) or (all([len(valid_tuple) == 4 for valid_tuple in valid_tuples]))
+        t = time.time()
+        if n_iter is None:
+            n_iter = self.num_iter_fit
+        loss = None
+        for itr in range(1, n_iter + 1):
+            task_idx = self._sample_task_indices()
+            self.optimizer.zero_grad()
+            loss = self.get_neg_elbo(task_idx)          # also fills .grad of the posterior parameters
+            self.optimizer.step()
+            self.lr_scheduler.step()
+            if itr == 1 or itr % log_period == 0:
+                eng.check_info(self._last_info)
+                duration = time.time() - t
+                t = time.time()
+                message = 'Iter %d/%d - Loss: %.6f - Time %.2f sec' % (itr, self.num_iter_fit, loss.item(), duration)
+                if valid_tuples is not None:
+                    valid_ll, valid_rmse, calibr_err = self.eval_datasets(valid_tuples)
+                    message += ' - Valid-LL: %.3f - Valid-RMSE: %.3f - Calib-Err %.3f' % (valid_ll, valid_rmse, calibr_err)
+                if verbose:
+                    self.logger.info(message)
+        self.fitted = True
+        return loss.item()
+
+    def _shard(self, task_idx):
+        idx = np.asarray(task_idx, dtype=np.int32)
+        T = idx.shape[0]
+        lo, hi = (self._rank * T) // self._world, ((self._rank + 1) * T) // self._world
+        return torch.from_numpy(idx[lo:hi].copy()).to(self.device), eng.pre_factor([self.engine.n] * T)
+
+    def get_neg_elbo(self, task_idx, eps=None):
+        """-mean_s [ log p(theta_s | data) - prior_factor * log q(theta_s) ] and its gradient w.r.t. the posterior
+        parameters (written to ``.grad``) -- the closure get_neg_elbo + loss.backward(), GPR_meta_vi.py:106-108, 216-224.
+        ``eps`` (S, D): optional caller-supplied standard-normal draws (parity tests); by default they come from
+        torch's global CPU generator exactly like ``posterior.rsample`` does in the reference."""
+        S, D = self.svi_batch_size, self.arch.D
+        idx_dev, pre = self._shard(task_idx)
+        if eps is None:
+            eps = torch.empty(S, D).normal_()                                   # Normal.rsample -> _standard_normal
+        eps = eps.to(self.device)
+        if self.cov_type == 'diag':
+            post = self.posterior
+            theta, logq = eng.vi_sample(post.loc.detach(), post.scale.detach(), eps)
+            logp, g, info = eng.meta_log_prob_and_score(theta, self.engine, idx_dev, self._prior_mu, self._prior_sigma,
+                                                        self.prior_factor, pre, self._group)
+            dloc, dscale = eng.vi_grad(post.scale.detach(), eps, g, self.prior_factor)
+            post.loc.grad, post.scale.grad = dloc, dscale
+            loss = -(logp - self.prior_factor * logq).mean()
+        else:
+            q = self.posterior.dist()
+            theta = self.posterior.loc + eps @ torch.tril(self.posterior.tril_cov).T      # MultivariateNormal.rsample
+            logp, info = eng.meta_log_prob(theta, self.engine, idx_dev, self._prior_mu, self._prior_sigma,
+                                           self.prior_factor, pre, self._group)
+            loss = -(logp - self.prior_factor * q.log_prob(theta)).mean()
+            loss.backward()
+            loss = loss.detach()
+        self._last_info = info
+        return loss
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, context_x, context_y, test_x, n_posterior_samples=100, mode='Bayes', return_density=False):
+        """Predictive distribution p(y | test_x, context) -- GPR_meta_vi.py:130-174."""
+        assert mode in ['bayes', 'Bayes', 'MAP', 'map']
+        mu, cov = self._predict_normalised(context_x, context_y, test_x, n_posterior_samples=n_posterior_samples, mode=mode)
+        if mode in ('Bayes', 'bayes'):
+            base = torch.distributions.MultivariateNormal(mu.cpu(), covariance_matrix=cov.cpu())
+            pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
+            pred_dist = EqualWeightedMixtureDist(pred_dist, batched=True)
+        else:
+            base = torch.distributions.MultivariateNormal(mu[0].cpu(), covariance_matrix=cov[0].cpu())   # GPR_meta_vi.py:252
+            pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
+        if return_density:
+            return pred_dist
+        return pred_dist.mean.numpy(), pred_dist.stddev.numpy()
+
+    def _sample_posterior(self, n):
+        """posterior.sample((n,)) from the CPU generator (GPR_meta_vi.py:236)."""
+        if self.cov_type == 'diag':
+            loc, std = self.posterior.loc.detach().cpu(), self.posterior.scale.detach().exp().cpu()
+            return torch.normal(loc.expand(n, -1), std.expand(n, -1)).to(self.device)
+        with torch.no_grad():
+            eps = torch.empty(n, self.arch.D).normal_().to(self.device)
+            return (self.posterior.loc + eps @ torch.tril(self.posterior.tril_cov).T).contiguous()
+
+    def _predict_normalised(self, context_x, context_y, test_x, n_posterior_samples=100, mode='Bayes'):
+        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
+        test_x = _handle_input_dimensionality(test_x)
+        assert test_x.shape[1] == context_x.shape[1]
+        xc, yc = self._prepare_data_per_task(context_x, context_y)
+        xs = torch.from_numpy(self._normalize_data(X=test_x, Y=None)).float().to(self.device)
+        with torch.no_grad():
+            if mode in ('Bayes', 'bayes'):
+                params = self._sample_posterior(n_posterior_samples)
+            else:
+                params = self.posterior.mode.view(1, -1).contiguous()
+            return eng.gp_posterior(self.arch, params.contiguous(), xc, yc, xs)
+
+    # ------------------------------------------------------------------ setup
+    def _setup_model_inference(self, mean_module_str, covar_module_str, mean_nn_layers, kernel_nn_layers, cov_type):
+        assert mean_module_str in ['NN', 'constant']
+        assert covar_module_str in ['NN', 'SE']
+        self.arch = eng.GPArch(self.input_dim, mean_kind=mean_module_str, covar_kind=covar_module_str,
+                               mean_layers=tuple(mean_nn_layers), kernel_layers=tuple(kernel_nn_layers), feature_dim=2)
+        prior_init.consume_vectorized_gp_init(self.arch)                          # RandomGPMeta.__init__ RNG draws
+        mu, sigma = self.arch.hyper_prior(self.weight_prior_std, self.bias_prior_std)
+        self._prior_mu, self._prior_sigma = mu.to(self.device), sigma.to(self.device)
+        if cov_type == 'diag':
+            loc, scale = prior_init.init_diag_posterior(self.arch.D)
+            self.posterior = _DiagPosterior(loc.to(self.device), scale.to(self.device), self.arch.entries())
+        else:
+            loc, tril = prior_init.init_full_posterior(self.arch.D)
+            self.posterior = _FullPosterior(loc.to(self.device), tril.to(self.device), self.arch.entries())
+
+    def _setup_optimizer(self, optimizer, lr, lr_decay):
+        if optimizer == 'Adam':
+            self.optimizer = eng.PacohAdam(self.posterior.parameters(), lr=lr)
+        elif optimizer == 'SGD':
+            self.optimizer = torch.optim.SGD(self.posterior.parameters(), lr=lr)
+        else:
+            raise NotImplementedError('Optimizer must be Adam or SGD')
+        if lr_decay < 1.0:
+            self.lr_scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, 1000, gamma=lr_decay)
+        else:
+            self.lr_scheduler = DummyLRScheduler()
+
+    def _vectorize_pred_dist(self, pred_dist):
+        mvn = pred_dist.dists
+        normal = torch.distributions.Normal(mvn.mean, mvn.stddev)
+        return EqualWeightedMixtureDist(normal, batched=True, num_dists=mvn.batch_shape[0])

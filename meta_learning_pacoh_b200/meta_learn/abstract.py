@@ -1,0 +1,160 @@
+"""Base class of the meta-learners: seeding, normalisation, per-task tensors and the evaluation API
+(eval / eval_datasets / confidence_intervals), call-compatible with meta_learn/abstract.py:117-272 of the reference.
+
+The evaluation metrics are computed on the device from the batched predictive mean / covariance the subclasses
+return in ``_predict_normalised`` -- the reference builds torch.distributions objects on the CPU and the same
+numbers fall out of them (abstract.py:157-161, models.py:15-43, 90-126).
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from .. import engine as eng
+from .distributions import AffineTransformedDistribution, EqualWeightedMixtureDist  # noqa: F401
+from .util import _handle_input_dimensionality, get_logger
+
+
+def default_device():
+    """CUDA device of this process: PACOH_DEVICE, else cuda:LOCAL_RANK, else cuda:0 (the reference's config.py:4
+    hard-codes cpu; this engine has no CPU path)."""
+    name = os.environ.get("PACOH_DEVICE")
+    if name:
+        return torch.device(name)
+    return torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+
+
+class RegressionModelMetaLearned:
+
+    def __init__(self, normalize_data=True, random_seed=None):
+        self.normalize_data = normalize_data
+        self.logger = get_logger()
+        self.input_dim = None
+        self.output_dim = None
+        self.device = default_device()
+        if random_seed is not None:           # abstract.py:125-129
+            torch.manual_seed(random_seed)
+            self.rds_numpy = np.random.RandomState(random_seed + 1)
+        else:
+            self.rds_numpy = np.random
+
+    # ------------------------------------------------------------------ public evaluation API
+    def predict(self, context_x, context_y, test_x, **kwargs):
+        raise NotImplementedError
+
+    def eval(self, context_x, context_y, test_x, test_y, flatten_y=True, **kwargs):
+        """(avg test log-likelihood, rmse, calibration error) on one task -- abstract.py:134-163."""
+        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
+        test_x, test_y = _handle_input_dimensionality(test_x, test_y)
+        assert flatten_y, "only scalar targets are supported"
+        mu, cov = self._predict_normalised(context_x, context_y, test_x, **kwargs)    # (P, n*), (P, n*, n*)
+        y = torch.from_numpy(test_y).float().flatten().to(self.device)
+        return self._metrics(mu, cov, y)
+
+    def eval_datasets(self, test_tuples, flatten_y=True, **kwargs):
+        """Average of eval() over test tasks -- abstract.py:165-181."""
+        assert all(len(t) == 4 for t in test_tuples)
+        res = [self.eval(*t, flatten_y=flatten_y, **kwargs) for t in test_tuples]
+        ll, rmse, cal = zip(*res)
+        return np.mean(ll), np.mean(rmse), np.mean(cal)
+
+    def confidence_intervals(self, context_x, context_y, test_x, confidence=0.9, **kwargs):
+        """(ucb, lcb) of the marginal predictive distribution -- abstract.py:183-204."""
+        pred_dist = self.predict(context_x, context_y, test_x, return_density=True, **kwargs)
+        pred_dist = self._vectorize_pred_dist(pred_dist)
+        alpha = (1 - confidence) / 2
+        shape = np.asarray(test_x).shape
+        ucb = pred_dist.icdf(torch.ones(shape) * (1 - alpha))
+        lcb = pred_dist.icdf(torch.ones(shape) * alpha)
+        return ucb, lcb
+
+    # ------------------------------------------------------------------ metrics on device
+    def _metrics(self, mu, cov, y):
+        P, ns = mu.shape
+        y_mean, y_std = float(self.y_mean[0]), float(self.y_std[0])
+        yn = (y - y_mean) / y_std
+        L, info = torch.linalg.cholesky_ex(cov)
+        if int(info.max().item()) > 0:
+            raise eng.NotPSDError("predictive covariance is not positive definite")
+        r = (yn.view(1, ns) - mu).unsqueeze(-1)
+        zs = torch.linalg.solve_triangular(L, r, upper=False).squeeze(-1)
+        logdet = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
+        lp = -0.5 * (zs ** 2).sum(-1) - 0.5 * logdet - 0.5 * ns * math.log(2 * math.pi) - ns * math.log(y_std)
+        ll = (torch.logsumexp(lp, 0) - math.log(P)) / ns
+        m = mu * y_std + y_mean
+        s = torch.sqrt(torch.diagonal(cov, dim1=-2, dim2=-1)) * y_std
+        rmse = torch.sqrt(torch.mean((m.mean(0) - y) ** 2))
+        cdf = (0.5 * (1 + torch.erf((y.view(1, ns) - m) / (s * math.sqrt(2.0))))).mean(0)
+        conf = torch.linspace(0.05, 0.95, 20, device=mu.device)
+        emp = (cdf[:, None] <= conf).sum(0).float() / ns
+        calib = torch.sqrt(torch.mean((emp - conf) ** 2))
+        out = torch.stack([ll, rmse, calib]).cpu()
+        return out[0].item(), out[1].item(), out[2].item()
+
+    # ------------------------------------------------------------------ data handling (abstract.py:212-258)
+    def _compute_normalization_stats(self, meta_train_tuples):
+        xs, ys = zip(*[_handle_input_dimensionality(x, y) for x, y in meta_train_tuples])
+        X, Y = np.concatenate(xs, axis=0), np.concatenate(ys, axis=0)
+        if self.normalize_data:
+            self.x_mean, self.y_mean = np.mean(X, axis=0), np.mean(Y, axis=0)
+            self.x_std, self.y_std = np.std(X, axis=0) + 1e-8, np.std(Y, axis=0) + 1e-8
+        else:
+            self.x_mean, self.y_mean = np.zeros(X.shape[1]), np.zeros(Y.shape[1])
+            self.x_std, self.y_std = np.ones(X.shape[1]), np.ones(Y.shape[1])
+
+    def _normalize_data(self, X, Y=None):
+        assert hasattr(self, "x_mean") and hasattr(self, "y_std"), "requires computing normalization stats beforehand"
+        Xn = (X - self.x_mean[None, :]) / self.x_std[None, :]
+        if Y is None:
+            return Xn
+        return Xn, (Y - self.y_mean[None, :]) / self.y_std[None, :]
+
+    def _check_meta_data_shapes(self, meta_train_data):
+        for i in range(len(meta_train_data)):
+            meta_train_data[i] = _handle_input_dimensionality(*meta_train_data[i])
+        self.input_dim = meta_train_data[0][0].shape[-1]
+        self.output_dim = meta_train_data[0][1].shape[-1]
+        assert all(self.input_dim == x.shape[-1] and self.output_dim == t.shape[-1] for x, t in meta_train_data)
+
+    def _prepare_data_per_task(self, x_data, y_data, flatten_y=True):
+        x_data, y_data = _handle_input_dimensionality(x_data, y_data)
+        x_data, y_data = self._normalize_data(x_data, y_data)
+        if flatten_y:
+            assert y_data.shape[1] == 1
+            y_data = y_data.flatten()
+        return torch.from_numpy(x_data).float().to(self.device), torch.from_numpy(y_data).float().to(self.device)
+
+    def _build_task_dicts(self, meta_train_data):
+        """Per-task tensors (task_dict['train_x'], ['train_y'] as in the reference) plus the stacked, device-resident
+        (T, n, d) / (T, n) arrays the kernels index with the sampled task ids."""
+        self.task_dicts = []
+        for train_x, train_y in meta_train_data:
+            x_t, y_t = self._prepare_data_per_task(train_x, train_y)
+            self.task_dicts.append({"train_x": x_t, "train_y": y_t})
+        sizes = {td["train_x"].shape[0] for td in self.task_dicts}
+        if len(sizes) != 1:
+            raise NotImplementedError("tasks with different numbers of points are not supported by the CUDA path yet "
+                                      "(SURVEY 8(f).3: ragged task batches)")
+        X = torch.stack([td["train_x"] for td in self.task_dicts])
+        Y = torch.stack([td["train_y"] for td in self.task_dicts])
+        return X, Y
+
+    def _sample_task_indices(self):
+        """rds_numpy.choice(self.task_dicts, size=B) of the reference (GPR_meta_svgd.py:102) draws the same index
+        stream as choice(len(task_dicts), size=B): sampling WITH replacement, duplicates count twice."""
+        return self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size)
+
+    def _calib_error(self, pred_dist_vectorized, test_t_tensor):
+        cdf_vals = pred_dist_vectorized.cdf(test_t_tensor)
+        if test_t_tensor.shape[0] == 1:
+            test_t_tensor, cdf_vals = test_t_tensor.flatten(), cdf_vals.flatten()
+        conf = torch.linspace(0.05, 0.95, 20)
+        emp = torch.sum(cdf_vals[:, None] <= conf, dim=0).float() / test_t_tensor.shape[0]
+        return torch.sqrt(torch.mean((emp - conf) ** 2))
+
+    def _vectorize_pred_dist(self, pred_dist):
+        raise NotImplementedError
+
+    def _predict_normalised(self, context_x, context_y, test_x, **kwargs):
+        raise NotImplementedError

@@ -1,0 +1,81 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/pacoh_b200.h declares, and its host-only
+entry points (layout / prior / workspace sizing / argument validation) behave.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from meta_learning_pacoh_b200 import _lib, engine as eng
+from oracle import pacoh_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "pacoh_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pacoh_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    names = _header_functions()
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names
+    for n in names:
+        assert hasattr(_lib.lib, n), n
+    assert _lib.lib.pacoh_abi_version() == 1
+
+
+def test_param_count_and_layout_match_reference(golden_dir):
+    import json
+    ref = json.load(open(os.path.join(golden_dir, "layout.json")))
+    cases = {"default_d1": eng.GPArch(1), "arch_d2": eng.GPArch(2, mean_layers=(16,), kernel_layers=(8, 24, 16)),
+             "const_se_d2": eng.GPArch(2, mean_kind="constant", covar_kind="SE")}
+    for key, arch in cases.items():
+        ent = arch.entries()
+        assert list(ent.keys()) == list(ref[key].keys())
+        assert [b - a for a, b in ent.values()] == [v[0] for v in ref[key].values()]
+    assert eng.GPArch(1).D == 2342
+    assert eng.GPArch(1, mean_layers=(32,) * 4, kernel_layers=(32,) * 4).D == 6566
+    assert eng.GPArch(1, outputscale=True, noise_floor=1e-3).D == 2343
+
+
+@pytest.mark.parametrize("kw", [dict(input_dim=1), dict(input_dim=3, mean_layers=(8, 8, 8), kernel_layers=(64,), feature_dim=5),
+                                dict(input_dim=2, mean_kind="constant", covar_kind="SE"),
+                                dict(input_dim=2, mean_kind="zero", covar_kind="NN")])
+def test_hyper_prior_params_match_oracle(kw):
+    arch = eng.GPArch(**kw)
+    okw = dict(kw)
+    lay = orc.Layout(**okw)
+    assert lay.D == arch.D
+    mu, sigma = arch.hyper_prior(0.4, 2.5)
+    mu2, sigma2 = orc.hyper_prior_params(lay, 0.4, 2.5)
+    assert torch.equal(mu, mu2) and torch.equal(sigma, sigma2)
+
+
+def test_pre_factor_matches_reference_formula():
+    assert abs(eng.pre_factor([5] * 20) - 5.0 / 25.0) < 1e-12
+    assert abs(eng.pre_factor([4, 12]) - orc.pre_factor([4, 12])) < 1e-15
+
+
+def test_argument_validation_and_workspace_sizes():
+    a = eng.GPArch(1).c_struct()
+    nbytes = _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 64, 4096, 50)
+    assert nbytes > 64 * 4096 * 50 * 4 * 6          # m, z(2), dm, dz(2)
+    assert nbytes < 2 * 1024 ** 3
+    assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 0, 4, 5) == _lib.PACOH_ERR_INVALID
+    assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 2, 4, 65) == _lib.PACOH_ERR_UNSUPPORTED
+    assert b"not implemented" in _lib.lib.pacoh_last_error()
+    bad = eng.GPArch(1).c_struct()
+    bad.mean_kind = 7
+    assert _lib.lib.pacoh_param_count(ctypes.byref(bad)) == _lib.PACOH_ERR_INVALID
+    with pytest.raises(_lib.PacohError):
+        _lib.check(_lib.lib.pacoh_svgd_phi(4, 10, None, None, 0.0, 0, None, None, None, 0, None))
+    assert _lib.lib.pacoh_svgd_workspace_bytes(64, 2342) >= 4 * (74 * 64 * 64 + 64 * 64 + 64)
+
+
+def test_engine_refuses_cpu_device():
+    with pytest.raises(RuntimeError):
+        eng.MetaMLLEngine(eng.GPArch(1), np.zeros((2, 5, 1), np.float32), np.zeros((2, 5), np.float32), device="cpu")

@@ -1,0 +1,307 @@
+"""GPU parity tests proper (``-m gpu``): the CUDA path, called through the C ABI, against
+  (a) the committed golden vectors produced by the live reference code (tests/golden/make_golden.py), and
+  (b) the CPU oracle (fp64) on the same seeded inputs,
+plus size-independent properties at BASELINE's full size (config #4: 64 particles x 4096 tasks x 50 points).
+
+Tolerance (north_star): 1e-4 relative on MLL, gradients, in fp32.  Gradients are compared per parameter group in
+the max-norm of the group (an entry whose true value is ~0, e.g. the kernel net's output bias, which the SE kernel
+is invariant to, has no meaningful element-wise relative error).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pacoh_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from meta_learning_pacoh_b200 import engine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return engine
+
+
+DEV = "cuda:0"
+
+ARCH = {
+    "svgd_cfg2.npz": (dict(input_dim=1), dict(input_dim=1)),
+    "svgd_n20.npz": (dict(input_dim=1), dict(input_dim=1)),
+    "svgd_arch.npz": (dict(input_dim=2, mean_layers=(16,), kernel_layers=(8, 24, 16)),) * 2,
+    "const_se.npz": (dict(input_dim=2, mean_kind="constant", covar_kind="SE"),) * 2,
+}
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def run_engine(eng, arch, x, y, theta, idx, prior_factor=0.01, wstd=0.5, bstd=3.0):
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    th = torch.as_tensor(theta, dtype=torch.float32).contiguous().to(DEV)
+    tidx = torch.as_tensor(np.asarray(idx), dtype=torch.int32).to(DEV)
+    mll, packed, info = e.mll_fwd_bwd(th, tidx)
+    mu, sigma = arch.hyper_prior(wstd, bstd)
+    pre = eng.pre_factor([x.shape[1]] * len(idx))
+    logp, dth = eng.logprob_finalize(th, mu.to(DEV), sigma.to(DEV), prior_factor, pre, packed)
+    return mll.cpu().numpy(), logp.cpu().numpy(), dth.cpu().numpy(), info.cpu().numpy()
+
+
+def oracle64(lay, x, y, theta, idx, prior_factor=0.01, wstd=0.5, bstd=3.0):
+    tasks = [(torch.from_numpy(np.asarray(x[i])).double(), torch.from_numpy(np.asarray(y[i])).double()) for i in range(len(x))]
+    mu, sigma = orc.hyper_prior_params(lay, wstd, bstd, torch.float64)
+    logp, g, mll = orc.meta_log_prob_and_grad(torch.as_tensor(theta).double(), lay, [tasks[i] for i in idx], prior_factor, mu, sigma)
+    return mll.numpy(), logp.numpy(), g.numpy()
+
+
+def assert_groups(arch, got, want, tol=RTOL):
+    """per parameter group, error in the group's max-norm; groups whose true gradient is (numerically) zero -- the kernel
+    net's output bias, to which the stationary SE kernel is invariant, only sees the tiny prior term -- are measured
+    against 1% of the overall gradient scale instead."""
+    scale = np.abs(want).max()
+    for name, (a, b) in arch.entries().items():
+        ref = want[:, a:b]
+        err = np.abs(got[:, a:b] - ref).max()
+        assert err <= tol * max(np.abs(ref).max(), 1e-2 * scale), (name, err, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", list(ARCH))
+def test_logp_and_score_match_reference_golden(eng, golden_dir, name):
+    fx = np.load(os.path.join(golden_dir, name))
+    arch = eng.GPArch(**ARCH[name][0])
+    mll, logp, score, info = run_engine(eng, arch, fx["x"], fx["y"], fx["particles"], fx["idx"])
+    assert (info == 0).all()
+    assert relmax(logp, fx["logp"]) <= RTOL
+    assert_groups(arch, score, fx["score"])
+    # and against the fp64 oracle, which is tighter than the reference's own fp32 run
+    lay = orc.Layout(**ARCH[name][1])
+    mll64, logp64, g64 = oracle64(lay, fx["x"], fx["y"], fx["particles"], fx["idx"])
+    assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
+    assert_groups(arch, score, g64)
+
+
+@pytest.mark.parametrize("name,bw", [("svgd_cfg2.npz", None), ("svgd_n20.npz", None), ("svgd_arch.npz", 0.7), ("const_se.npz", None)])
+def test_svgd_phi_matches_reference_golden(eng, golden_dir, name, bw):
+    fx = np.load(os.path.join(golden_dir, name))
+    P, D = fx["particles"].shape
+    sv = eng.SVGDDirection(P, D, DEV, bandwidth=bw)
+    phi = sv(torch.from_numpy(fx["particles"]).to(DEV), torch.from_numpy(fx["score"]).to(DEV))
+    assert abs(float(sv.gamma.item()) - float(fx["gamma"])) <= 1e-5 * float(fx["gamma"])
+    assert relmax(phi.cpu().numpy(), fx["phi"]) <= RTOL
+
+
+def test_vi_sample_and_gradient_match_reference_golden(eng, golden_dir):
+    fx = np.load(os.path.join(golden_dir, "vi_cfg3.npz"))
+    arch = eng.GPArch(1)
+    loc, scale, eps = (torch.from_numpy(fx[k]).to(DEV) for k in ("loc", "scale", "eps"))
+    theta, logq = eng.vi_sample(loc, scale, eps)
+    assert np.abs(theta.cpu().numpy() - fx["theta"]).max() <= 1e-6
+    assert relmax(logq.cpu().numpy(), fx["logq"]) <= 1e-5
+    T = fx["x"].shape[0]
+    e = eng.MetaMLLEngine(arch, fx["x"], fx["y"], DEV)
+    mu, sigma = arch.hyper_prior(0.5, 3.0)
+    tidx = torch.arange(T, dtype=torch.int32, device=DEV)
+    _, packed, info = e.mll_fwd_bwd(theta, tidx)
+    logp, g = eng.logprob_finalize(theta, mu.to(DEV), sigma.to(DEV), 0.01, eng.pre_factor([20] * T), packed)
+    loss = -(logp - 0.01 * logq).mean()
+    assert abs(loss.item() - float(fx["loss"])) <= RTOL * abs(float(fx["loss"]))
+    dloc, dscale = eng.vi_grad(scale, eps, g, 0.01)
+    assert relmax(dloc.cpu().numpy(), fx["dloc"]) <= RTOL
+    assert relmax(dscale.cpu().numpy(), fx["dscale"]) <= RTOL
+
+
+# ------------------------------------------------------------------------------------------ oracle, edge cases
+def _synthetic(T, n, d=1, seed=0):
+    rs = np.random.RandomState(seed)
+    x = rs.uniform(-2, 2, size=(T, n, d)).astype(np.float32)
+    y = (np.sin(2 * x[..., 0]) + 0.1 * rs.normal(size=(T, n))).astype(np.float32)
+    return x, y
+
+
+def _prior_particles(lay, P, seed):
+    mu, sigma = orc.hyper_prior_params(lay, 0.5, 3.0)
+    g = torch.Generator().manual_seed(seed)
+    return (mu + sigma * torch.randn(P, lay.D, generator=g)).numpy()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 20, 31, 32, 33, 40, 47, 48, 49, 50, 52, 63, 64])
+def test_every_matrix_size_up_to_64(eng, n):
+    """all NC instantiations of the warp-per-matrix kernel, ragged last tile of the MLP kernels, repeated tasks."""
+    x, y = _synthetic(5, n, seed=n)
+    lay, arch = orc.Layout(1), eng.GPArch(1)
+    theta = _prior_particles(lay, 3, 100 + n)
+    idx = [4, 0, 0, 3, 1, 4, 2]
+    mll, logp, score, info = run_engine(eng, arch, x, y, theta, idx)
+    mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
+    assert (info == 0).all()
+    assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
+    assert_groups(arch, score, g64)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(input_dim=1, mean_layers=(32,), kernel_layers=(32,)),
+    dict(input_dim=1, mean_layers=(32, 32, 32), kernel_layers=(32, 32, 32)),
+    dict(input_dim=1, mean_layers=(32,) * 4, kernel_layers=(32,) * 4),
+    dict(input_dim=3, mean_layers=(32, 32), kernel_layers=(32, 32), feature_dim=4),
+    dict(input_dim=2, mean_layers=(32, 32), kernel_layers=(16, 16), feature_dim=1),           # different depths / widths
+    dict(input_dim=1, mean_layers=(64, 64), kernel_layers=(32, 32)),                         # generic + fast mixed
+    dict(input_dim=6, mean_layers=(20, 12), kernel_layers=(40,), feature_dim=7),              # generic: d > 4, F > 4
+    dict(input_dim=2, mean_kind="zero", covar_kind="NN"),
+    dict(input_dim=3, mean_kind="NN", covar_kind="SE"),
+    dict(input_dim=1, outputscale=True, noise_floor=1e-3),                                    # PACOH-MAP variant
+])
+def test_architectures_match_oracle(eng, kw):
+    d = kw["input_dim"]
+    x, y = _synthetic(6, 13, d=d, seed=3)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    assert lay.D == arch.D
+    theta = _prior_particles(lay, 4, 7)
+    idx = [5, 1, 1, 0, 2, 3, 4, 4]
+    mll, logp, score, info = run_engine(eng, arch, x, y, theta, idx)
+    mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
+    assert (info == 0).all()
+    assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
+    assert_groups(arch, score, g64)
+
+
+def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
+    """BASELINE config #1: the engine's P=1 ScaleRBF/noise-floor path reproduces demo.ipynb's 'Loss: 5.755850'."""
+    train = orc.sinusoid_tasks(20, 5, seed=26)
+    m = orc.MAPOracle(train, weight_decay=0.2, seed=30)
+    kw = dict(input_dim=1, outputscale=True, noise_floor=1e-3)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    theta = m.flat_parameters(lay)
+    x = np.stack([t[0].numpy() for t in m.tasks]); y = np.stack([t[1].numpy() for t in m.tasks])
+    idx = [18, 16, 2, 6, 10]
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    mll, packed, info = e.mll_fwd_bwd(theta.to(DEV), torch.tensor(idx, dtype=torch.int32, device=DEV))
+    loss = -float(packed[-1].item())
+    assert "%.5f" % loss == "5.75585"
+    # gradient of the MAP loss w.r.t. the torch modules, packed into the flat layout
+    total = 0.0
+    for i in idx:
+        total = total - m.mll(*m.tasks[i])
+    total.backward()
+    g_ref = torch.zeros(lay.D)
+    for prefix, net in (("mean_nn", m.mean_nn), ("kernel_nn", m.kernel_nn)):
+        lin = [mod for mod in net if isinstance(mod, torch.nn.Linear)]
+        names = ["fc_%d" % (k + 1) for k in range(len(lin) - 1)] + ["out"]
+        for nm, l in zip(names, lin):
+            a, b = lay.entries["%s.%s.bias" % (prefix, nm)]; g_ref[a:b] = l.bias.grad
+            a, b = lay.entries["%s.%s.weight" % (prefix, nm)]; g_ref[a:b] = l.weight.grad.reshape(-1)
+    a, b = lay.entries["lengthscale_raw"]; g_ref[a:b] = m.raw_lengthscale.grad.reshape(-1)
+    a, b = lay.entries["noise_raw"]; g_ref[a:b] = m.raw_noise.grad
+    a, b = lay.entries["outputscale_raw"]; g_ref[a:b] = m.raw_outputscale.grad.reshape(1)
+    got = -packed[:lay.D].cpu().numpy().reshape(1, -1)
+    assert_groups(arch, got, g_ref.numpy().reshape(1, -1), tol=2e-4)
+
+
+def test_jitter_ladder_and_not_psd_reporting(eng):
+    """duplicate inputs + vanishing noise: singular K.  The kernel must climb the 1e-6/1e-5/1e-4 jitter ladder
+    (gpytorch psd_safe_cholesky) or report failure; the host wrapper raises NotPSDError on failure."""
+    arch = eng.GPArch(1, mean_kind="zero", covar_kind="SE")
+    x = np.zeros((2, 8, 1), np.float32)             # all points identical -> rank-1 Gram
+    x[1] = np.linspace(-1, 1, 8, dtype=np.float32).reshape(8, 1)
+    y = np.ones((2, 8), np.float32)
+    theta = np.zeros((2, arch.D), np.float32)
+    theta[0, arch.entries()["noise_raw"][0]] = -40.0      # softplus(-40) ~ 4e-18
+    theta[1, arch.entries()["noise_raw"][0]] = 0.0
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    mll, packed, info = e.mll_fwd_bwd(torch.from_numpy(theta).to(DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))
+    info = info.cpu().numpy()
+    assert info[1, 0] == 0 and info[1, 1] == 0           # healthy particle untouched
+    assert info[0, 0] != 0                               # singular matrix needed jitter (or failed)
+    if (info < 0).any():
+        with pytest.raises(eng.NotPSDError):
+            eng.check_info(torch.from_numpy(info))
+    else:
+        assert np.isfinite(mll.cpu().numpy()).all()
+
+
+def test_unsupported_sizes_fail_loudly(eng):
+    from meta_learning_pacoh_b200._lib import PacohError
+    arch = eng.GPArch(1)
+    x, y = _synthetic(2, 80)
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    with pytest.raises(PacohError):
+        e.mll_fwd_bwd(torch.zeros(2, arch.D, device=DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))
+    with pytest.raises(NotImplementedError):
+        eng.SVGDDirection(4, 10, DEV, kernel="IMQ")
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+@pytest.fixture(scope="module")
+def config4(eng):
+    P, T, n = 64, 4096, 50
+    train = orc.sinusoid_tasks(T, n, seed=26)
+    stats = orc.normalization_stats(train)
+    x = np.stack([(a - stats[0]) / stats[1] for a, _ in train]).astype(np.float32)
+    y = np.stack([((b - stats[2]) / stats[3]).reshape(-1) for _, b in train]).astype(np.float32)
+    lay, arch = orc.Layout(1), eng.GPArch(1)
+    theta = torch.from_numpy(_prior_particles(lay, P, 30)).to(DEV)
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    idx = np.random.RandomState(31).choice(T, size=T).astype(np.int32)
+    return dict(P=P, T=T, n=n, x=x, y=y, lay=lay, arch=arch, theta=theta, e=e, idx=idx)
+
+
+def test_full_size_deterministic_and_sharding_is_linear(eng, config4):
+    c = config4
+    tidx = torch.from_numpy(c["idx"]).to(DEV)
+    mll_a, packed_a, info = c["e"].mll_fwd_bwd(c["theta"], tidx)
+    mll_b, packed_b, _ = c["e"].mll_fwd_bwd(c["theta"], tidx)
+    assert int(info.min()) == 0 and int(info.max()) == 0
+    assert torch.equal(packed_a, packed_b) and torch.equal(mll_a, mll_b)          # bitwise repeatable
+    assert torch.isfinite(packed_a).all()
+    # task sharding (multi-GPU decomposition): the sum over 4 shards equals the full batch
+    acc = torch.zeros_like(packed_a, dtype=torch.float64)
+    for s in range(4):
+        _, pk, _ = c["e"].mll_fwd_bwd(c["theta"], tidx[s * 1024:(s + 1) * 1024].contiguous())
+        acc += pk.double()
+    scale = packed_a.abs().max().item()
+    assert (acc - packed_a.double()).abs().max().item() <= 2e-5 * scale
+    # per-task values do not depend on the batch they are evaluated in
+    mll_s, _, _ = c["e"].mll_fwd_bwd(c["theta"], tidx[:1024].contiguous())
+    assert torch.equal(mll_s, mll_a[:, :1024])
+
+
+def test_full_size_spot_check_against_oracle(eng, config4):
+    """64 x 4096 x 50 is too big for the CPU oracle; check a random subset of (particle, task) values in fp64 and
+    the gradient on a 32-task sub-batch (size-independent: the kernels process a task identically in any batch)."""
+    c = config4
+    tidx = torch.from_numpy(c["idx"]).to(DEV)
+    mll, _, _ = c["e"].mll_fwd_bwd(c["theta"], tidx)
+    mll = mll.cpu().numpy()
+    rs = np.random.RandomState(0)
+    th64 = c["theta"].cpu().double()
+    for t in rs.choice(c["T"], size=6, replace=False):
+        src = c["idx"][t]
+        ref = orc.task_mll(th64, c["lay"], torch.from_numpy(c["x"][src]).double(), torch.from_numpy(c["y"][src]).double()).numpy()
+        assert np.abs(mll[:, t] - ref).max() <= RTOL * np.abs(ref).max()
+    sub = c["idx"][:32]
+    P8 = 8
+    _, logp, score, _ = run_engine(eng, c["arch"], c["x"], c["y"], c["theta"][:P8].cpu().numpy(), sub)
+    _, logp64, g64 = oracle64(c["lay"], c["x"], c["y"], c["theta"][:P8].cpu().numpy(), sub)
+    assert relmax(logp, logp64) <= RTOL
+    assert_groups(c["arch"], score, g64)
+
+
+def test_full_size_svgd_direction_properties(eng, config4):
+    c = config4
+    P, D = c["theta"].shape
+    score = torch.randn(P, D, device=DEV)
+    sv = eng.SVGDDirection(P, D, DEV)
+    phi = sv(c["theta"], score)
+    ref, gamma = orc.svgd_phi(c["theta"].cpu().double(), score.cpu().double())
+    assert abs(float(sv.gamma.item()) - gamma) <= 1e-5 * gamma
+    assert relmax(phi.cpu().numpy(), ref.numpy()) <= RTOL
+    # permutation equivariance: permuting the particles permutes phi
+    perm = torch.randperm(P, device=DEV)
+    phi_p = sv(c["theta"][perm].contiguous(), score[perm].contiguous())
+    assert (phi_p - phi[perm]).abs().max().item() <= 1e-5 * phi.abs().max().item()

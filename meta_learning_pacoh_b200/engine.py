@@ -126,6 +126,12 @@ def pre_factor(task_sizes) -> float:
     return float(hm / (hm + len(sizes)))
 
 
+def shard_bounds(T, rank, world):
+    """Contiguous slice [lo, hi) of a length-T sampled task batch owned by `rank` (the batch index list,
+    duplicates included, is split into `world` contiguous chunks)."""
+    return (rank * T) // world, ((rank + 1) * T) // world
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 

@@ -94,7 +94,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         ``task_idx``: numpy / sequence of task indices into the meta-training set (with repetitions)."""
         idx = np.asarray(task_idx, dtype=np.int32)
         T = idx.shape[0]
-        lo, hi = (self._rank * T) // self._world, ((self._rank + 1) * T) // self._world
+        lo, hi = eng.shard_bounds(T, self._rank, self._world)
         if self._idx_host.numel() < hi - lo:
             self._idx_host = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
         self._idx_host[:hi - lo].copy_(torch.from_numpy(idx[lo:hi]))
@@ -118,7 +118,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         holding the sampled, normalised batch in order.  They are copied to the device, the step runs on them with
         identity task indices, and logp (P,) is returned on the host.  Used for the end-to-end measurement."""
         T = x_batch.shape[0]
-        lo, hi = (self._rank * T) // self._world, ((self._rank + 1) * T) // self._world
+        lo, hi = eng.shard_bounds(T, self._rank, self._world)
         if getattr(self, "_stage_engine", None) is None or self._stage_engine.T_total != hi - lo:
             xs = torch.empty((hi - lo,) + tuple(x_batch.shape[1:]), dtype=torch.float32)
             ys = torch.empty((hi - lo,) + tuple(y_batch.shape[1:]), dtype=torch.float32)

@@ -135,7 +135,7 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
     def _shard(self, task_idx):
         idx = np.asarray(task_idx, dtype=np.int32)
         T = idx.shape[0]
-        lo, hi = (self._rank * T) // self._world, ((self._rank + 1) * T) // self._world
+        lo, hi = eng.shard_bounds(T, self._rank, self._world)
         return torch.from_numpy(idx[lo:hi].copy()).to(self.device), eng.pre_factor([self.engine.n] * T)
 
     def get_neg_elbo(self, task_idx, eps=None):

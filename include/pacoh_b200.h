@@ -156,8 +156,10 @@ int pacoh_adam_step(int64_t count, float* param, const float* grad, float grad_s
 int pacoh_stage_timing_enable(int32_t on);
 int pacoh_stage_timing_read(float* ms_out, int32_t* calls_out);
 
-/* FP32 FFMA micro-benchmark used by bench.py for the roofline denominator: runs `iters` dependent-chain
- * FFMA blocks on every SM and returns the number of floating-point operations issued in *flops_out (host). */
+/* FP32 FFMA micro-benchmark used by bench.py for the roofline denominator.  iters > 0: immediate-operand dependent
+ * chains (the classic peak test); iters < 0: |iters| iterations of a GEMM-shaped body whose FFMAs read three distinct
+ * registers (acc += w * v), the form the kernels actually issue.  `sink` needs >= 20 floats.  The number of
+ * floating-point operations issued is returned in *flops_out (host). */
 int pacoh_ffma_peak_launch(int32_t iters, float* sink, double* flops_out, void* stream);
 
 #ifdef __cplusplus

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -91,6 +92,17 @@ static int mlp_chunks(int P, int nets, int Q) {
   return std::max(1, std::min(by_waves, by_work));
 }
 
+// The MLP forward runs on the tensor cores (mlp_tc.cu, 3xTF32 tcgen05) unless PACOH_MLP_FWD=ffma selects the
+// CUDA-core kernel of mlp.cu (kept for A/B measurements; both are parity-tested).
+static bool use_tc_forward() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PACOH_MLP_FWD");
+    v = (e != nullptr && strcmp(e, "ffma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 struct Plan {
   ModelDev m;
   int Q, chunks;
@@ -165,6 +177,35 @@ __global__ void ffma_peak_kernel(int iters, float* sink) {
   if (s == 12345.678f) sink[0] = s;   // never true: keeps the chains alive
 }
 
+// GEMM-shaped variant: 32 accumulators, every FFMA reads three distinct registers (acc += w[e] * v[i]) with runtime
+// operands -- the form the MLP / GP kernels issue, as opposed to the immediate-operand chains above.
+__global__ void ffma_peak_gemm_kernel(int iters, float* sink) {
+  float acc[8][4], w[8], v[4];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    w[e] = sink[8 + e] + threadIdx.x * 1e-6f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[e][i] = 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = sink[16 + i];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[e][i] = fmaf(w[e], v[i], acc[e][i]);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += acc[e][i];
+  if (s == 12345.678f) sink[0] = s;
+}
+
 }  // namespace pacoh
 
 using namespace pacoh;
@@ -233,7 +274,7 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
       ma.out[0] = ws + pl.off_mean; ma.out[1] = ws + pl.off_feat;
       ma.dout[0] = ws + pl.off_dmean; ma.dout[1] = ws + pl.off_dfeat;
       ma.partial[0] = ws + pl.off_pmean; ma.partial[1] = ws + pl.off_pkern;
-      return launch_mlp_fast(ma, 2, pl.chunks, bwd, st);
+      return (!bwd && use_tc_forward()) ? launch_mlp_tc_fwd(ma, 2, pl.chunks, st) : launch_mlp_fast(ma, 2, pl.chunks, bwd, st);
     }
     for (int z = 0; z < 2; ++z) {
       const bool is_nn = z == 0 ? pl.mean_nn : pl.kern_nn;
@@ -243,7 +284,8 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
       ma.dout[0] = ws + (z == 0 ? pl.off_dmean : pl.off_dfeat);
       ma.partial[0] = ws + (z == 0 ? pl.off_pmean : pl.off_pkern);
       const bool fast = z == 0 ? pl.mean_fast : pl.kern_fast;
-      int r = fast ? launch_mlp_fast(ma, 1, pl.chunks, bwd, st) : launch_mlp_generic(ma, 0, pl.chunks, bwd, ws + pl.off_gen, st);
+      int r = fast ? ((!bwd && use_tc_forward()) ? launch_mlp_tc_fwd(ma, 1, pl.chunks, st) : launch_mlp_fast(ma, 1, pl.chunks, bwd, st))
+                   : launch_mlp_generic(ma, 0, pl.chunks, bwd, ws + pl.off_gen, st);
       if (r != PACOH_OK) return r;
     }
     return PACOH_OK;
@@ -311,7 +353,8 @@ extern "C" int pacoh_gp_forward(const pacoh_arch_t* arch, int32_t P, int32_t npt
     ma.net[0] = z == 0 ? m.mean : m.kern;
     ma.out[0] = dst;
     const bool fast = z == 0 ? pl.mean_fast : pl.kern_fast;
-    rc = fast ? launch_mlp_fast(ma, 1, chunks, false, st) : launch_mlp_generic(ma, 0, 1, false, (float*)workspace, st);
+    rc = fast ? (use_tc_forward() ? launch_mlp_tc_fwd(ma, 1, chunks, st) : launch_mlp_fast(ma, 1, chunks, false, st))
+              : launch_mlp_generic(ma, 0, 1, false, (float*)workspace, st);
     if (rc != PACOH_OK) return rc;
   }
   return PACOH_OK;
@@ -340,10 +383,15 @@ extern "C" int pacoh_stage_timing_read(float* ms_out, int32_t* calls_out) {
 }
 
 extern "C" int pacoh_ffma_peak_launch(int32_t iters, float* sink, double* flops_out, void* stream) {
-  if (iters < 1 || !sink) { set_error("pacoh_ffma_peak_launch: invalid argument"); return PACOH_ERR_INVALID; }
+  if (iters == 0 || !sink) { set_error("pacoh_ffma_peak_launch: invalid argument"); return PACOH_ERR_INVALID; }
   const int blocks = sm_count() * 8, threads = 256;
-  ffma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+  if (iters > 0) {   // immediate-operand dependent chains
+    ffma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (flops_out) *flops_out = 2.0 * (double)blocks * threads * (double)iters * 16.0 * 8.0;
+  } else {           // iters < 0: GEMM-shaped three-register form, |iters| iterations (sink needs >= 20 floats)
+    ffma_peak_gemm_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(-iters, sink);
+    if (flops_out) *flops_out = 2.0 * (double)blocks * threads * (double)(-iters) * 4.0 * 32.0;
+  }
   PACOH_CUDA_CHECK(cudaGetLastError());
-  if (flops_out) *flops_out = 2.0 * (double)blocks * threads * (double)iters * 16.0 * 8.0;
   return PACOH_OK;
 }

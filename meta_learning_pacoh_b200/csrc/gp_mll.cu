@@ -74,6 +74,102 @@ __device__ __forceinline__ void block_columns(const float (&A)[NS][NC], float (&
 #undef PACOH_BLK_CASE
 }
 
+// ---- building blocks of the blocked sweep (all register / warp-local) -----------------------------------------
+// Publish the 4 block columns (= the 4 pivot rows, by symmetry) and the pivot rows' augmented entries.  The pivot
+// block's own diagonal is published MINUS 1: with X = B0 - I in place of B0 the uniform rank-4 update also produces
+// the swept values of the block columns themselves, so the register matrix never needs a dynamic-index write-back.
+template <int NS>
+__device__ __forceinline__ void publish_block(float* pb, float (&t0)[NS][4], const float (&dadd)[NS], const float (&aug)[NS],
+                                              int lane, int c) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int rel = lane + 32 * s - 4 * c;       // position of this row inside the block (0..3) if it is a pivot row
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (rel == j) t0[s][j] += dadd[s];         // true diagonal (deferred unit-diagonal term)
+      pb[j * kPubStride + lane + 32 * s] = rel == j ? t0[s][j] - 1.0f : t0[s][j];
+    }
+    if (rel >= 0 && rel < 4) pb[4 * kPubStride + rel] = aug[s];
+  }
+}
+
+__device__ __forceinline__ void load_pivot_block(const float* pb, int c, float (&B)[4][4], float4& augB) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = lds4(pb + j * kPubStride + 4 * c);
+    B[j][0] = v.x; B[j][1] = v.y; B[j][2] = v.z; B[j][3] = v.w;
+    B[j][j] += 1.0f;
+  }
+  augB = lds4(pb + 4 * kPubStride);
+}
+
+// In-register symmetric sweep of the 4x4 pivot block: B <- -B^-1; its pivots are the Schur diagonals d_k = L_kk^2.
+__device__ __forceinline__ void invert4(float (&B)[4][4], bool& ok, float& logdet2) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float d = B[q4][q4];
+    ok = ok && (d > 1e-12f);
+    logdet2 += lg2_approx(d);
+    const float inv = rcp_newton(d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i == q4) continue;
+      const float f = B[i][q4] * inv;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j != q4) B[i][j] = fmaf(-f, B[q4][j], B[i][j]);
+      B[i][q4] = f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j != q4) B[q4][j] *= inv;
+    B[q4][q4] = -inv;
+  }
+}
+
+// Row multipliers of the rank-4 update (Binv = -B): non-pivot rows w = t0 Binv; pivot rows w = e_rel - Binv[rel][:].
+template <int NS>
+__device__ __forceinline__ void multipliers(float (&w)[NS][4], const float (&t0)[NS][4], const float (&B)[4][4], int lane, int c) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int rel = lane + 32 * s - 4 * c;
+    const bool inb = rel >= 0 && rel < 4;
+    float uu[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uu[j] = -(t0[s][0] * B[0][j] + t0[s][1] * B[1][j] + t0[s][2] * B[2][j] + t0[s][3] * B[3][j]);
+      if (inb) uu[j] = rel == j ? 1.0f : 0.0f;   // B0[rel][:] Binv = e_rel exactly (no cond(B0) rounding)
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float uB = -(uu[0] * B[0][j] + uu[1] * B[1][j] + uu[2] * B[2][j] + uu[3] * B[3][j]);
+      w[s][j] = inb ? uu[j] - uB : uu[j];
+    }
+  }
+}
+
+// A[s][col] -= sum_j w[s][j] * X[j][col] over the whole row (a pivot row's own diagonal register ends up at
+// -Binv_rr + 2 - dadd: undone when the diagonal is read).
+template <int NC, int NS>
+__device__ __forceinline__ void rank4_update(float (&A)[NS][NC], const float (&w)[NS][4], const float* pb) {
+#pragma unroll
+  for (int c4 = 0; c4 < NC / 4; ++c4) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = lds4(pb + j * kPubStride + 4 * c4);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        A[s][4 * c4] = fmaf(-w[s][j], v[j].x, A[s][4 * c4]);
+        A[s][4 * c4 + 1] = fmaf(-w[s][j], v[j].y, A[s][4 * c4 + 1]);
+        A[s][4 * c4 + 2] = fmaf(-w[s][j], v[j].z, A[s][4 * c4 + 2]);
+        A[s][4 * c4 + 3] = fmaf(-w[s][j], v[j].w, A[s][4 * c4 + 3]);
+      }
+    }
+  }
+}
+
 template <int NC, int FT>
 __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kernel(GpArgs a) {
   constexpr int NS = (NC + 31) / 32;
@@ -171,96 +267,54 @@ __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kerne
       dadd[s] = valid[s] ? 1.0f - rho : 1.0f;
     }
 
-    // ---- blocked symmetric Gauss-Jordan sweep, 4 pivots per block
+    // ---- blocked symmetric Gauss-Jordan sweep, 4 pivots per block, software pipelined:
+    //      iteration c publishes + inverts block c+1 (a latency-bound dependent chain) in the same basic block as the
+    //      416 independent FFMAs of block c's rank-4 update, so ptxas interleaves the two.
     bool ok = true;
     logdet2 = 0.0f;
-#pragma unroll 1
-    for (int c = 0; c < NB; ++c) {
-      if (4 * c >= n) break;                         // only identity padding left
-      float* pb = s_pub[warp][c & 1];
-      float t0[NS][4];
-      block_columns<NC, NS>(A, t0, c);
-      // publish the block columns (= the 4 pivot rows, by symmetry).  The pivot block's own diagonal is published
-      // minus 1: with X = B0 - I in place of B0 the uniform rank-4 update below also produces the swept values of
-      // the block columns themselves, so the register matrix never needs a dynamic-index write-back.
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const int rel = lane + 32 * s - 4 * c;       // position of this row inside the block (0..3) if it is a pivot row
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rel == j) t0[s][j] += dadd[s];         // true diagonal (deferred unit-diagonal term)
-          pb[j * kPubStride + lane + 32 * s] = rel == j ? t0[s][j] - 1.0f : t0[s][j];
-        }
-        if (rel >= 0 && rel < 4) pb[4 * kPubStride + rel] = aug[s];
-      }
+    const int nblk = (n + 3) >> 2;
+    float w[NS][4];
+    float4 augB;
+    {
+      float t0[NS][4], B[4][4];
+      block_columns<NC, NS>(A, t0, 0);
+      publish_block<NS>(s_pub[warp][0], t0, dadd, aug, lane, 0);
       __syncwarp();
-      // ---- 4x4 pivot block (rows 4c..4c+3 of the published columns), inverted redundantly by every lane
-      float B[4][4];
+      load_pivot_block(s_pub[warp][0], 0, B, augB);
+      invert4(B, ok, logdet2);
+      multipliers<NS>(w, t0, B, lane, 0);
+    }
+#pragma unroll 1
+    for (int c = 0; c < nblk && ok; ++c) {
+      const float* pb = s_pub[warp][c & 1];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 v = lds4(pb + j * kPubStride + 4 * c);
-        B[j][0] = v.x; B[j][1] = v.y; B[j][2] = v.z; B[j][3] = v.w;
-        B[j][j] += 1.0f;
-      }
-      const float4 augB = lds4(pb + 4 * kPubStride);
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {               // in-register sweep: B <- -B^-1, pivots = Schur diagonals
-        const float d = B[q4][q4];
-        ok = ok && (d > 1e-12f);
-        logdet2 += lg2_approx(d);
-        const float inv = rcp_newton(d);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i == q4) continue;
-          const float f = B[i][q4] * inv;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j != q4) B[i][j] = fmaf(-f, B[q4][j], B[i][j]);
-          B[i][q4] = f;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j != q4) B[q4][j] *= inv;
-        B[q4][q4] = -inv;
-      }
-      if (!ok) break;                                 // warp-uniform (every lane inverted the same block)
-      // ---- multipliers (Binv = -B): non-pivot rows w = t0 Binv; pivot rows w = e_rel - Binv[rel][:]
-      float w[NS][4];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const int rel = lane + 32 * s - 4 * c;
-        const bool inb = rel >= 0 && rel < 4;
-        float uu[4];
+      for (int s = 0; s < NS; ++s) aug[s] -= w[s][0] * augB.x + w[s][1] * augB.y + w[s][2] * augB.z + w[s][3] * augB.w;
+      if (c + 1 < nblk) {
+        float* pbn = s_pub[warp][(c + 1) & 1];
+        float tn[NS][4], B[4][4];
+        block_columns<NC, NS>(A, tn, c + 1);
+        // bring the next block's columns up to date with block c's update before everything else
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uu[j] = -(t0[s][0] * B[0][j] + t0[s][1] * B[1][j] + t0[s][2] * B[2][j] + t0[s][3] * B[3][j]);
-          if (inb) uu[j] = rel == j ? 1.0f : 0.0f;   // B0[rel][:] Binv = e_rel exactly (no cond(B0) rounding)
-        }
+          const float4 x4 = lds4(pb + j * kPubStride + 4 * (c + 1));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float uB = -(uu[0] * B[0][j] + uu[1] * B[1][j] + uu[2] * B[2][j] + uu[3] * B[3][j]);
-          w[s][j] = inb ? uu[j] - uB : uu[j];
-        }
-        aug[s] -= w[s][0] * augB.x + w[s][1] * augB.y + w[s][2] * augB.z + w[s][3] * augB.w;
-      }
-      // ---- rank-4 update of every row:  A[s][col] -= sum_j w[s][j] * X[j][col]
-      //      (a pivot row's own diagonal register ends up at  -Binv_rr + 2 - dadd : undone when the diagonal is read)
-#pragma unroll
-      for (int c4 = 0; c4 < NC / 4; ++c4) {
-        float4 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = lds4(pb + j * kPubStride + 4 * c4);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            A[s][4 * c4] = fmaf(-w[s][j], v[j].x, A[s][4 * c4]);
-            A[s][4 * c4 + 1] = fmaf(-w[s][j], v[j].y, A[s][4 * c4 + 1]);
-            A[s][4 * c4 + 2] = fmaf(-w[s][j], v[j].z, A[s][4 * c4 + 2]);
-            A[s][4 * c4 + 3] = fmaf(-w[s][j], v[j].w, A[s][4 * c4 + 3]);
+          for (int s = 0; s < NS; ++s) {
+            tn[s][0] = fmaf(-w[s][j], x4.x, tn[s][0]); tn[s][1] = fmaf(-w[s][j], x4.y, tn[s][1]);
+            tn[s][2] = fmaf(-w[s][j], x4.z, tn[s][2]); tn[s][3] = fmaf(-w[s][j], x4.w, tn[s][3]);
           }
         }
+        publish_block<NS>(pbn, tn, dadd, aug, lane, c + 1);
+        __syncwarp();
+        float4 augBn;
+        load_pivot_block(pbn, c + 1, B, augBn);
+        invert4(B, ok, logdet2);                      // dependent chain ...
+        rank4_update<NC, NS>(A, w, pb);               // ... overlapped with block c's independent FFMAs
+        multipliers<NS>(w, tn, B, lane, c + 1);
+        augB = augBn;
+      } else {
+        rank4_update<NC, NS>(A, w, pb);
       }
+      __syncwarp();   // all lanes are done reading pb before the buffer is republished two blocks later
     }
     __syncwarp();
     if (ok) status = attempt;

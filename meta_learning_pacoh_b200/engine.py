@@ -288,15 +288,16 @@ def vi_grad(scale, eps, g, prior_factor):
     return dloc, dscale
 
 
-def ffma_peak_tflops(iters=4096, reps=5):
-    """Measured FP32 FFMA throughput of the device (TFLOP/s): the FP32 roofline denominator reported by bench.py."""
-    sink = torch.zeros(4, dtype=torch.float32, device="cuda")
+def ffma_peak_tflops(iters=4096, reps=5, gemm_form=False):
+    """Measured FP32 FFMA throughput of the device (TFLOP/s): the FP32 roofline denominator reported by bench.py.
+    gemm_form=False: immediate-operand chains (peak); True: three-register acc += w * v form."""
+    sink = torch.zeros(32, dtype=torch.float32, device="cuda")
     flops = ctypes.c_double(0.0)
     best = 0.0
     for _ in range(reps + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(lib.pacoh_ffma_peak_launch(iters, _ptr(sink), ctypes.byref(flops), _stream()))
+        check(lib.pacoh_ffma_peak_launch(-iters if gemm_form else iters, _ptr(sink), ctypes.byref(flops), _stream()))
         e1.record()
         e1.synchronize()
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)

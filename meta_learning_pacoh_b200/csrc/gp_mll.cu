@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kGpWarps = 4;
 #ifndef PACOH_GP_MINB
-#define PACOH_GP_MINB(NC) ((NC) > 32 ? 2 : 4)   // min CTAs per SM: 2 x 4 warps with the full register matrix, no spills
+#define PACOH_GP_MINB(NC) ((NC) > 32 ? 3 : 4)   // min CTAs per SM (EXPERIMENT: 3 -> 168 regs, some spills)
 #endif
 constexpr int kPubStride = 68;            // floats per published block column (64 rows + pad)
 constexpr int kPubFloats = 4 * kPubStride + 8;   // 4 columns + 4 augmented entries of the pivot rows (+ pad)

@@ -102,6 +102,20 @@ static bool use_tc_forward() {
   }
   return v == 1;
 }
+static bool use_tc_backward() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PACOH_MLP_BWD");
+    v = (e != nullptr && strcmp(e, "ffma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+// forward / backward of `nets` register-tiled-capable nets: tensor-core kernels by default
+static int launch_mlp_best(const MlpArgs& ma, int nets, int chunks, bool bwd, cudaStream_t st) {
+  if (!bwd && use_tc_forward()) return launch_mlp_tc_fwd(ma, nets, chunks, st);
+  if (bwd && use_tc_backward()) return launch_mlp_tc_bwd(ma, nets, chunks, st);
+  return launch_mlp_fast(ma, nets, chunks, bwd, st);
+}
 
 struct Plan {
   ModelDev m;
@@ -274,7 +288,7 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
       ma.out[0] = ws + pl.off_mean; ma.out[1] = ws + pl.off_feat;
       ma.dout[0] = ws + pl.off_dmean; ma.dout[1] = ws + pl.off_dfeat;
       ma.partial[0] = ws + pl.off_pmean; ma.partial[1] = ws + pl.off_pkern;
-      return (!bwd && use_tc_forward()) ? launch_mlp_tc_fwd(ma, 2, pl.chunks, st) : launch_mlp_fast(ma, 2, pl.chunks, bwd, st);
+      return launch_mlp_best(ma, 2, pl.chunks, bwd, st);
     }
     for (int z = 0; z < 2; ++z) {
       const bool is_nn = z == 0 ? pl.mean_nn : pl.kern_nn;
@@ -284,7 +298,7 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
       ma.dout[0] = ws + (z == 0 ? pl.off_dmean : pl.off_dfeat);
       ma.partial[0] = ws + (z == 0 ? pl.off_pmean : pl.off_pkern);
       const bool fast = z == 0 ? pl.mean_fast : pl.kern_fast;
-      int r = fast ? ((!bwd && use_tc_forward()) ? launch_mlp_tc_fwd(ma, 1, pl.chunks, st) : launch_mlp_fast(ma, 1, pl.chunks, bwd, st))
+      int r = fast ? launch_mlp_best(ma, 1, pl.chunks, bwd, st)
                    : launch_mlp_generic(ma, 0, pl.chunks, bwd, ws + pl.off_gen, st);
       if (r != PACOH_OK) return r;
     }

@@ -136,19 +136,28 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
   const int t0 = blockIdx.x * per, t1 = min(tiles, t0 + per);
   float* outp = a.out[blockIdx.z] + (size_t)p * Q * net.out_dim;
 
+  // inputs of the NEXT tile are loaded one tile ahead (global latency hidden behind the current tile)
+  auto load_x = [&](int tile_i, float (&xo)[DIN]) {
+    const int qq = tile_i * kTcTile + tid;
+    const bool ok = tile_i < t1 && qq < Q;
+    int src = 0;
+    if (ok) {
+      const int t = qq / a.n;
+      src = (a.task_idx != nullptr ? __ldg(a.task_idx + t) : t) * a.n + (qq - t * a.n);
+    }
+#pragma unroll
+    for (int dd = 0; dd < DIN; ++dd) xo[dd] = (ok && dd < a.d) ? __ldg(a.x + (size_t)src * a.d + dd) : 0.0f;
+  };
+  float xn[DIN];
+  load_x(t0, xn);
+
   for (int tile = t0; tile < t1; ++tile) {
     const int q = tile * kTcTile + tid;
     const bool valid = q < Q;
     float x[DIN];
-    {
-      int src = 0;
-      if (valid) {
-        const int t = q / a.n;
-        src = (a.task_idx != nullptr ? __ldg(a.task_idx + t) : t) * a.n + (q - t * a.n);
-      }
 #pragma unroll
-      for (int dd = 0; dd < DIN; ++dd) x[dd] = (valid && dd < a.d) ? __ldg(a.x + (size_t)src * a.d + dd) : 0.0f;
-    }
+    for (int dd = 0; dd < DIN; ++dd) x[dd] = xn[dd];
+    load_x(tile + 1, xn);
     // ---- layer 1 (input dim <= 4): registers only
     float h[kHid];
 #pragma unroll

@@ -305,3 +305,14 @@ def test_full_size_svgd_direction_properties(eng, config4):
     perm = torch.randperm(P, device=DEV)
     phi_p = sv(c["theta"][perm].contiguous(), score[perm].contiguous())
     assert (phi_p - phi[perm]).abs().max().item() <= 1e-5 * phi.abs().max().item()
+
+
+def test_cuda_core_mlp_kernels_still_match_oracle():
+    """The FFMA versions of the MLP kernels (mlp.cu) are selected by PACOH_MLP_FWD/BWD=ffma (read once per process):
+    run them in a subprocess against the fp64 oracle so both implementations stay parity-green."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PACOH_MLP_FWD="ffma", PACOH_MLP_BWD="ffma")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ffma_path_check.py")
+    r = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr

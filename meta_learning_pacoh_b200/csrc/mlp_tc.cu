@@ -4,71 +4,34 @@
 // UMMA instructions issued by one thread per CTA:
 //
 //   tile   = 128 points of the flattened task batch; thread t of the CTA owns point t for the elementwise work
-//   A      = H_{l-1} tile (128 x 32, K-major, SWIZZLE_NONE core-matrix layout) written to shared memory by the threads
-//   B      = W_l (32 x 32, K-major) staged once per CTA
+//   A      = H_{l-1} tile (128 x 32): each thread writes its row into ITS TENSOR-MEMORY LANE with tcgen05.st (hi / lo parts),
+//            so activations never touch shared memory (no proxy fence, no bank conflicts)
+//   B      = W_l (32 x 32, K-major SWIZZLE_NONE core-matrix layout in shared memory) staged once per CTA
 //   D      = 128 lanes x 32 fp32 columns in tensor memory; read back with tcgen05.ld (lane == point), bias + tanh in registers
 //
 // Precision: the north-star asks for 1e-4 relative parity on gradients in fp32, which plain TF32 (10-bit mantissa)
 // cannot give.  Every operand is therefore split into hi = tf32(v) and lo = v - hi and the product is accumulated as
-// lo*hi + hi*lo + hi*hi in fp32 (3xTF32): ~4e-7 relative error measured against fp64 (tools/ubench/tc_gemm_test.cu),
-// at 12 tcgen05.mma instructions per layer and tile -- still ~5x less tensor-pipe time than the FFMA version needs issue
-// slots, and it frees the CUDA cores for tanh / splitting / the output layer.
+// lo*hi + hi*lo + hi*hi in fp32 (3xTF32): ~4e-7 relative error measured against fp64 (tools/ubench/tc_ts_test.cu),
+// at 12 tcgen05.mma instructions per layer and tile (~17.6 cycles each), and it frees the CUDA cores for tanh /
+// splitting / the output layer.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace pacoh {
 
 namespace {
 
+using namespace tc;
+
 constexpr int kTcThreads = 128;
 constexpr int kTcTile = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// SWIZZLE_NONE K-major shared-memory matrix descriptor: start address, leading (K-chunk) and stride (8-row group) byte offsets.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  return d;
-}
-
-// kind::tf32 instruction descriptor: fp32 accumulate, both operands K-major, M x N tile.
-__device__ __forceinline__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-
-// float offset of element (row r, k) in a K-major SWIZZLE_NONE tile with R rows and 32 K-elements:
-// 16-byte chunk index = r + (k / 4) * R   (8-row groups are contiguous: SBO = 128 B; K-chunk planes: LBO = 16 R bytes)
-__device__ __forceinline__ int ktile_off(int r, int k, int R) { return ((r + (k >> 2) * R) << 2) + (k & 3); }
+constexpr int kFwdMinSmemBytes = 56 * 1024;   // caps residency at 4 CTAs/SM = 4 x 128 TMEM columns (the whole tensor memory)
 
 template <int L, int DIN, int OUT>
 struct TcSmem {
   // floats
-  static constexpr int A_HI = 0;                                   // [128 x 32] activation tile, hi parts
-  static constexpr int A_LO = A_HI + kTcTile * kHid;
-  static constexpr int B = A_LO + kTcTile * kHid;                  // per hidden layer l = 2..L: W hi [32x32], W lo [32x32]
+  static constexpr int B = 0;                                      // per hidden layer l = 2..L: W hi [32x32], W lo [32x32]
   static constexpr int W1 = B + (L - 1) * 2 * kHid * kHid;         // [32][DIN]
   static constexpr int B1 = W1 + kHid * DIN;
   static constexpr int BH = B1 + kHid;                             // biases of layers 2..L
@@ -87,14 +50,8 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
   const int p = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
   const float* th = a.theta + (size_t)p * a.D;
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" :: "r"(smem_u32(&tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;");
-  }
+  if (warp == 0) tmem_alloc<kTmemCols>(&tmem_base_s);
+  if (tid == 0) mbar_init(smem_u32(&mbar), 1);
   // ---- stage the particle's weights: hidden-layer matrices as K-major UMMA B operands (hi / lo), the rest as plain arrays
   const int w0 = net.width[0];
   for (int i = tid; i < kHid * DIN; i += kTcThreads) {
@@ -121,12 +78,12 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
     smem[S::WOUT + i] = (o < net.out_dim && k < wl) ? th[net.off_w[L] + o * wl + k] : 0.0f;
   }
   if (tid < 4) smem[S::BOUT + tid] = tid < net.out_dim ? th[net.off_b[L] + tid] : 0.0f;
-  asm volatile("fence.proxy.async.shared::cta;");
-  asm volatile("tcgen05.fence::before_thread_sync;");
+  fence_async_smem();            // generic-proxy writes of the B operands -> visible to the tensor-core proxy
+  fence_before_sync();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;");
+  fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 TMEM lanes
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
   const uint32_t bar = smem_u32(&mbar);
   uint32_t parity = 0;
 
@@ -174,47 +131,19 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
     // ---- hidden layers 2..L on the tensor cores
 #pragma unroll
     for (int l = 2; l <= L; ++l) {
-      // write this point's activations as row `tid` of the A tile (hi / lo), 16-byte chunks: conflict-free STS.128
-#pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        float hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(h[4 * kc + e]); lo[e] = h[4 * kc + e] - hi[e]; }
-        sts4(smem + S::A_HI + ((tid + kc * kTcTile) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts4(smem + S::A_LO + ((tid + kc * kTcTile) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
-      }
-      asm volatile("fence.proxy.async.shared::cta;");      // generic-proxy writes -> visible to the tensor-core proxy
-      asm volatile("tcgen05.fence::before_thread_sync;");
+      store_a_tmem(lane_base, h);          // this point's activations -> its TMEM lane (hi / lo)
+      fence_before_sync();
       __syncthreads();
       if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t idesc = umma_idesc_tf32(128, 32);
-        const uint32_t a_hi = smem_u32(smem + S::A_HI), a_lo = smem_u32(smem + S::A_LO);
-        const uint32_t b_hi = smem_u32(smem + S::B + (l - 2) * 2 * kHid * kHid), b_lo = b_hi + kHid * kHid * 4;
-        uint32_t acc = 0;
-#pragma unroll
-        for (int ps = 0; ps < 3; ++ps) {                    // lo*hi, hi*lo, hi*hi
-          const uint32_t sa = ps == 0 ? a_lo : a_hi, sb = ps == 1 ? b_lo : b_hi;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {                  // K = 32 = 4 x 8
-            umma_tf32(tmem, umma_desc(sa + ks * 2 * kTcTile * 16, kTcTile * 16, 128),
-                      umma_desc(sb + ks * 2 * kHid * 16, kHid * 16, 128), idesc, acc);
-            acc = 1;
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+        fence_after_sync();
+        const uint32_t b_hi = smem_u32(smem + S::B + (l - 2) * 2 * kHid * kHid);
+        gemm128x32x32_3xtf32_ts(tmem, b_hi, b_hi + kHid * kHid * 4, bar);
       }
       mbar_wait(bar, parity);
       parity ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;");
+      fence_after_sync();
       uint32_t v[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-            "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-            "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld32(lane_base + kTmemD, v);
 #pragma unroll
       for (int j4 = 0; j4 < kHid; j4 += 4) {
         const float4 b = lds4(smem + S::BH + (l - 2) * kHid + j4);
@@ -236,15 +165,16 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
       if (valid && o < net.out_dim) outp[(size_t)q * net.out_dim + o] = acc;
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;");
+  fence_before_sync();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" :: "r"(tmem));
+  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
 template <int L, int DIN, int OUT>
 int launch_tc(const MlpArgs& a, int chunks, int nets, cudaStream_t st) {
   using S = TcSmem<L, DIN, OUT>;
-  const size_t smem = sizeof(float) * S::END;
+  size_t smem = sizeof(float) * S::END;
+  if (smem < (size_t)kFwdMinSmemBytes) smem = kFwdMinSmemBytes;
   PACOH_CUDA_CHECK(cudaFuncSetAttribute(mlp_tc_fwd_kernel<L, DIN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(chunks, a.P, nets);
   mlp_tc_fwd_kernel<L, DIN, OUT><<<grid, kTcThreads, smem, st>>>(a);

@@ -3,7 +3,7 @@
 // Same semantics as mlp_bwd_kernel in mlp.cu (the autograd reverse pass through NeuralNetworkVectorized,
 // meta_learn/models.py:295-317, 343-349, svgd.py:16).  Work split per 128-point tile (thread t owns point t):
 //
-//   tensor cores (tcgen05, 3xTF32, D in TMEM)          CUDA cores
+//   tensor cores (tcgen05, 3xTF32, A and D in TMEM)    CUDA cores
 //   -------------------------------------------          -----------------------------------------------------------------
 //   H_l   = tanh(H_{l-1} W_l^T + b_l)   (recompute)      layer 1, tanh, hi/lo splitting, output-layer backward
 //   dH_{l-1} = dA_l W_l                                  dW_l += dA_l^T H_{l-1}  as a 32x32x32 warp GEMM over the warp's own 32
@@ -29,9 +29,7 @@ constexpr int kTF = kHid * kSRow;   // floats of one per-warp [32 features][36] 
 
 template <int L, int DIN, int OUT>
 struct BwdSmem {
-  static constexpr int A_HI = 0;                                   // [128 x 32] K-major tile, hi parts
-  static constexpr int A_LO = A_HI + kTile * kHid;
-  static constexpr int B = A_LO + kTile * kHid;                    // per layer l = 2..L: W hi, W lo, W^T hi, W^T lo (1024 floats each)
+  static constexpr int B = 0;                                      // per layer l = 2..L: W hi, W lo, W^T hi, W^T lo (1024 floats each)
   static constexpr int W1 = B + (L - 1) * 4 * kHid * kHid;         // [32][DIN]
   static constexpr int B1 = W1 + kHid * DIN;
   static constexpr int BH = B1 + kHid;                             // biases of layers 2..L
@@ -44,7 +42,7 @@ struct BwdSmem {
   static constexpr int DOUT = X + DIN * 32;                        // [OUT][32]
   static constexpr int WARP_SIZE = DOUT + 4 * ((OUT * 32 + 3) / 4);
   static constexpr int END = WARP + kWarps * WARP_SIZE;
-  // padded accumulator layout for the in-CTA reduction (aliases the A tiles): b1, W1, (b_l, W_l) l = 2..L, bout, Wout
+  // padded accumulator layout for the in-CTA reduction (aliases the per-warp regions): b1, W1, (b_l, W_l) l = 2..L, bout, Wout
   static constexpr int R_B1 = 0;
   static constexpr int R_W1 = kHid;
   static constexpr int R_H = R_W1 + kHid * DIN;
@@ -52,23 +50,11 @@ struct BwdSmem {
   static constexpr int R_BO = R_H + (L - 1) * R_HSTRIDE;
   static constexpr int R_WO = R_BO + OUT;
   static constexpr int R_END = R_WO + OUT * kHid;
-  static_assert(R_END <= 2 * kTile * kHid, "reduction buffer must fit in the A tiles");
+  static_assert(R_END <= kWarps * WARP_SIZE, "reduction buffer must fit in the per-warp regions");
 };
 
-// write this point's 32 values as row `row` of the K-major A tiles (hi / lo): conflict-free STS.128
-__device__ __forceinline__ void store_a_tiles(float* a_hi, float* a_lo, const float (&h)[kHid], int row) {
-#pragma unroll
-  for (int kc = 0; kc < 8; ++kc) {
-    float hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(h[4 * kc + e]); lo[e] = h[4 * kc + e] - hi[e]; }
-    sts4(a_hi + ((row + kc * kTile) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
-    sts4(a_lo + ((row + kc * kTile) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
-  }
-}
-
 template <int L, int DIN, int OUT>
-__global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
   using S = BwdSmem<L, DIN, OUT>;
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t mbar;
@@ -78,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
   const float* th = a.theta + (size_t)p * a.D;
   float* sw = smem + S::WARP + warp * S::WARP_SIZE;   // this warp's region
 
-  if (warp == 0) tmem_alloc<32>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<kTmemCols>(&tmem_base_s);
   if (tid == 0) mbar_init(smem_u32(&mbar), 1);
   // ---- stage the particle's weights
   const int w0 = net.width[0];
@@ -113,9 +99,8 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
   const uint32_t bar = smem_u32(&mbar);
-  const uint32_t a_hi = smem_u32(smem + S::A_HI), a_lo = smem_u32(smem + S::A_LO);
   uint32_t parity = 0;
 
   // ---- persistent accumulators
@@ -193,20 +178,19 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
       float* Tprev = sw + S::T + (l - 2) * kTF;
 #pragma unroll
       for (int k = 0; k < kHid; ++k) Tprev[k * kSRow + lane] = h[k];
-      store_a_tiles(smem + S::A_HI, smem + S::A_LO, h, tid);
-      fence_async_smem();
+      store_a_tmem(lane_base, h);                   // A operand of the recompute GEMM: this point's row -> its TMEM lane
       fence_before_sync();
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
         const uint32_t b_hi = smem_u32(smem + S::B + (l - 2) * 4 * kHid * kHid);
-        gemm128x32x32_3xtf32(tmem, a_hi, a_lo, b_hi, b_hi + kHid * kHid * 4, bar);
+        gemm128x32x32_3xtf32_ts(tmem, b_hi, b_hi + kHid * kHid * 4, bar);
       }
       mbar_wait(bar, parity);
       parity ^= 1;
       fence_after_sync();
       uint32_t v[32];
-      tmem_ld32(taddr, v);
+      tmem_ld32(lane_base + kTmemD, v);
 #pragma unroll
       for (int j4 = 0; j4 < kHid; j4 += 4) {
         const float4 b = lds4(smem + S::BH + (l - 2) * kHid + j4);
@@ -250,14 +234,13 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
       __syncwarp();                                 // every lane is done reading H_l^T
 #pragma unroll
       for (int k = 0; k < kHid; ++k) Tl[k * kSRow + lane] = da[k];
-      store_a_tiles(smem + S::A_HI, smem + S::A_LO, da, tid);
-      fence_async_smem();
+      store_a_tmem(lane_base, da);
       fence_before_sync();
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
         const uint32_t bt_hi = smem_u32(smem + S::B + (l - 2) * 4 * kHid * kHid + 2 * kHid * kHid);
-        gemm128x32x32_3xtf32(tmem, a_hi, a_lo, bt_hi, bt_hi + kHid * kHid * 4, bar);     // dH_{l-1} = dA_l W_l
+        gemm128x32x32_3xtf32_ts(tmem, bt_hi, bt_hi + kHid * kHid * 4, bar);              // dH_{l-1} = dA_l W_l
       }
       // ---- while the MMA runs: dW_l += dA_l^T H_{l-1} over this warp's 32 points, and db_l
       {
@@ -289,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
       parity ^= 1;
       fence_after_sync();
       uint32_t v[32];
-      tmem_ld32(taddr, v);
+      tmem_ld32(lane_base + kTmemD, v);
       __syncwarp();                                 // the warp GEMM above is done reading H_{l-1}^T
 #pragma unroll
       for (int k = 0; k < kHid; ++k) {
@@ -325,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
   for (int o = 0; o < OUT; ++o) accbo[o] = warp_sum(accbo[o]);
   fence_before_sync();
   __syncthreads();
-  float* sacc = smem + S::A_HI;
+  float* sacc = smem + S::WARP;
   for (int i = tid; i < S::R_END; i += kThreads) sacc[i] = 0.0f;
   __syncthreads();
   for (int w = 0; w < kWarps; ++w) {
@@ -372,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_tc_bwd_kernel(MlpArgs a) {
     dst[i] = sacc[src];
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc<32>(tmem);
+  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
 template <int L, int DIN, int OUT>

@@ -74,6 +74,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Store 16 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // float offset of element (row r, k) in a K-major SWIZZLE_NONE tile with R rows and 32 K-elements:
@@ -91,6 +100,54 @@ __device__ __forceinline__ void gemm128x32x32_3xtf32(uint32_t tmem, uint32_t a_h
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {   // K = 32 = 4 x 8
       umma_tf32(tmem, umma_desc(sa + ks * 2 * 128 * 16, 128 * 16, 128), umma_desc(sb + ks * 2 * 32 * 16, 32 * 16, 128), idesc, acc);
+      acc = 1;
+    }
+  }
+  umma_commit(bar);
+}
+
+// ---- A operand in TENSOR MEMORY ("TS" form): row r of the 128 x 32 A tile lives in TMEM lane r, columns [col, col+32).
+// TMEM column map used by the MLP kernels (128 columns allocated per CTA):
+constexpr uint32_t kTmemD = 0;      // accumulator D (32 fp32 columns)
+constexpr uint32_t kTmemAhi = 32;   // A operand, tf32 hi parts
+constexpr uint32_t kTmemAlo = 64;   // A operand, lo parts
+constexpr int kTmemCols = 128;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// This thread's 32 activations -> hi / lo split -> its TMEM lane (columns kTmemAhi.. / kTmemAlo..): no shared memory,
+// no proxy fence, no bank conflicts.  `lane_base` = tmem base + (first lane of the warp << 16).
+__device__ __forceinline__ void store_a_tmem(uint32_t lane_base, const float (&h)[32]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float v = h[16 * c + e], hv = tf32_hi(v);
+      hi[e] = __float_as_uint(hv);
+      lo[e] = __float_as_uint(v - hv);
+    }
+    tmem_st16(lane_base + kTmemAhi + 16 * c, hi);
+    tmem_st16(lane_base + kTmemAlo + 16 * c, lo);
+  }
+  tmem_st_wait();
+}
+
+// D[128 x 32] = A[128 x 32] * B[32 x 32]^T in 3xTF32 with A in TMEM, B (hi / lo, 32-row K-major tiles) in shared memory.
+__device__ __forceinline__ void gemm128x32x32_3xtf32_ts(uint32_t tmem, uint32_t b_hi, uint32_t b_lo, uint32_t bar) {
+  const uint32_t idesc = umma_idesc_tf32(128, 32);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int ps = 0; ps < 3; ++ps) {                    // lo*hi, hi*lo, hi*hi
+    const uint32_t a_col = ps == 0 ? kTmemAlo : kTmemAhi, sb = ps == 1 ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {                  // K = 32 = 4 x 8 (8 TMEM columns per step)
+      umma_tf32_ts(tmem + kTmemD, tmem + a_col + ks * 8, umma_desc(sb + ks * 2 * 32 * 16, 32 * 16, 128), idesc, acc);
       acc = 1;
     }
   }

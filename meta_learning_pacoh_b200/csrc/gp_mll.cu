@@ -478,6 +478,14 @@ int dispatch_nc4_f2(const GpArgs& a, cudaStream_t st) {
 
 int launch_gp_mll(const GpArgs& a, cudaStream_t st) {
   if (a.n < 1 || a.n > kMaxGpN || a.F < 1 || a.F > kMaxGpF) return PACOH_ERR_UNSUPPORTED;
+  // 32 < n <= 64: the tensor-memory / tcgen05 kernel (gp_tc.cu) unless PACOH_GP=warp selects the register kernel
+  // (kept for A/B measurements; both are parity-tested).
+  static int tc = -1;
+  if (tc < 0) {
+    const char* e = getenv("PACOH_GP");
+    tc = (e != nullptr && strcmp(e, "warp") == 0) ? 0 : 1;
+  }
+  if (tc == 1 && a.n > 32 && a.F <= 4) return launch_gp_mll_tc(a, st);
   if (a.F <= 2) return dispatch_nc4_f2(a, st);
   if (a.F <= 4) return dispatch_nc16<4>(a, st);
   return dispatch_nc16<16>(a, st);

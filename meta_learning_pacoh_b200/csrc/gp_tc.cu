@@ -1,0 +1,380 @@
+// Batched GP marginal log-likelihood with analytic gradient -- tensor-memory / tcgen05 version for 32 < n <= 64, sm_100a.
+//
+// Same mathematics and outputs as gp_mll_kernel (gp_mll.cu; reference: meta_learn/random_gp.py:54-89, models.py:428-487,
+// gpytorch ExactMarginalLogLikelihood at random_gp.py:83-85 and its autograd reverse pass, svgd.py:16), different mapping:
+//
+//   CTA = 128 threads = TWO (particle, task) matrices; thread (m = tid >> 6, row = tid & 63) owns one matrix row.
+//   The normalised matrix lives in TENSOR MEMORY: row r of matrix m is TMEM lane 64 m + r, columns 0..63 (fp32).
+//   Blocked symmetric Gauss-Jordan, 4 pivots per block.  Per block
+//     1. every thread reads its 4 block-column entries with tcgen05.ld at a RUNTIME column offset (tensor memory is
+//        addressed, registers are not: no register-indexing switch), adds the deferred diagonal term and publishes them
+//        as one 16-byte chunk of the UMMA B operand X[64 x 8] (K-slots 0-3: matrix 0, 4-7: matrix 1; hi / lo split);
+//     2. after a CTA barrier every thread inverts its matrix's 4x4 pivot block in registers (pivots = squared
+//        Cholesky diagonal: same log det / positive-definiteness test), forms its row multipliers w and publishes -w
+//        as its row of the UMMA A operand W[128 x 8] (zeros in the other matrix's K-slots);
+//     3. ONE thread issues the rank-4 update of BOTH matrices, D[128 x 64] += W X^T, as 3 tcgen05.mma (3xTF32,
+//        fp32 accumulate in place in TMEM) -- the 2 x 416 FFMAs per block of the register version disappear.
+//   The `X - I` trick (pivot block diagonal published minus 1) makes the same uniform update produce the swept block
+//   columns; a pivot row's own diagonal ends up offset by 2 - dadd, undone when the diagonal is read.
+#include <math_constants.h>
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace pacoh {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kGT = 128;           // threads per CTA
+constexpr int kRows = 64;          // rows per matrix
+constexpr float kFar = 1.0e18f;    // scaled feature of a padding row: exp2(-(1e18)^2) == 0 exactly
+constexpr int kGpTmemCols = 64;
+#ifndef PACOH_GPTC_MINB
+#define PACOH_GPTC_MINB 6   // CTAs per SM the register allocation is capped for (tensor memory allows 8)
+#endif
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpn(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r * fmaf(-d, r, 2.0f); }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&f)[8]) {
+  uint32_t v[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+}
+
+// In-register symmetric sweep of the 4x4 pivot block: B <- -B^-1 (only the upper triangle B[i][j], i <= j, is read or
+// written; the swept matrix stays symmetric); its pivots are the Schur diagonals d_k = L_kk^2.
+#define PACOH_SYM(i, j) B[(i) < (j) ? (i) : (j)][(i) < (j) ? (j) : (i)]
+__device__ __forceinline__ void invert4_sym(float (&B)[4][4], bool& ok, float& logdet2) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float d = B[q4][q4];
+    ok = ok && (d > 1e-12f);
+    logdet2 += lg2a(d);
+    const float inv = rcpn(d);
+    float f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = i == q4 ? 0.0f : PACOH_SYM(i, q4) * inv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i; j < 4; ++j)
+        if (i != q4 && j != q4) B[i][j] = fmaf(-f[i], PACOH_SYM(q4, j), B[i][j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i != q4) PACOH_SYM(i, q4) = f[i];
+    B[q4][q4] = -inv;
+  }
+}
+
+template <int FT>
+__global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
+  constexpr int RS = ((FT + 1 + 3) / 4) * 4;   // smem feature row: FT scaled features, then alpha
+  __shared__ __align__(1024) float s_x_hi[kRows * 8], s_x_lo[kRows * 8];     // UMMA B operand X [64 x 8], K-major
+  __shared__ __align__(1024) float s_w_hi[kGT * 8], s_w_lo[kGT * 8];         // UMMA A operand W [128 x 8], K-major
+  __shared__ __align__(16) float s_t0[2][kRows][4];                          // published block columns (true values)
+  __shared__ __align__(16) float s_aug[2][4];
+  __shared__ __align__(16) float s_feat[2][kRows][RS];
+  __shared__ float s_red[2][2][8];                                           // [matrix][warp-in-matrix][slot]
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mtx = tid >> 6, row = tid & 63, wim = warp & 1;
+  const int pairs = a.P * a.T;
+  const int pair = blockIdx.x * 2 + mtx;
+  const bool pvalid = pair < pairs;
+  const int pr = pvalid ? pair : pairs - 1;
+  const int p = pr / a.T, t = pr - p * a.T;
+  const int n = a.n, F = a.F, Q = a.T * a.n;
+  const int src = __ldg(a.task_idx + t);
+  const float* th = a.theta + (size_t)p * a.D;
+  float(*sf)[RS] = s_feat[mtx];
+
+  if (warp == 0) tmem_alloc<kGpTmemCols>(&tmem_base_s);
+  if (tid == 0) mbar_init(smem_u32(&mbar), 1);
+  // the K-slots of the OTHER matrix are zero in this row of W, for the whole kernel
+  sts4(s_w_hi + ((tid + (1 - mtx) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+  sts4(s_w_lo + ((tid + (1 - mtx) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+
+  // ---- hyper-parameters (random_gp.py:69-73; MAP: GPR_meta_mll.py:54-55,218)
+  const float kC = 0.84932180028801904272f;   // sqrt(0.5 * log2(e))
+  const float raw_noise = __ldg(th + a.off_noise);
+  const float sig2 = a.noise_floor + softplus_f(raw_noise);
+  const float raw_os = a.has_oscale ? __ldg(th + a.off_oscale) : 0.0f;
+  const float osc = a.has_oscale ? softplus_f(raw_os) : 1.0f;
+
+  // ---- this thread's row: residual and scaled features (padding rows sit "infinitely far" away => zero Gram rows)
+  const bool valid = row < n;
+  const size_t q = (size_t)p * Q + (size_t)t * n + row;
+  float r = 0.0f, u[FT];
+  {
+    float m = a.mean_kind == PACOH_MEAN_CONSTANT ? __ldg(th + a.off_const_mean) : 0.0f;
+    if (a.mean != nullptr && valid) m = __ldg(a.mean + q);
+    r = valid ? __ldg(a.y + (size_t)src * n + row) - m : 0.0f;
+#pragma unroll
+    for (int f = 0; f < FT; ++f) {
+      float z = 0.0f;
+      if (valid && f < F) z = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * n + row) * a.d + f);
+      const float inv_ls = f < F ? kC / softplus_f(__ldg(th + a.off_ls + f)) : 0.0f;
+      u[f] = valid ? z * inv_ls : kFar;
+    }
+#pragma unroll
+    for (int f = 0; f < RS; ++f) sf[row][f] = f < FT ? u[f] : 0.0f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t bar = smem_u32(&mbar);
+  uint32_t parity = 0;
+  const int nblk = (n + 3) >> 2;       // 4-pivot blocks
+  const int ngrp = (n + 7) >> 3;       // 8-column groups of the row that are ever read
+  const uint32_t idesc = umma_idesc_tf32(128, ((n + 15) >> 4) << 4);
+
+  float aug = 0.0f, tot = 0.0f, rho = 0.0f, logdet2 = 0.0f, dadd = 0.0f;
+  int lvl = 0, status = -1;     // jitter level of this thread's matrix (uniform within the matrix)
+#pragma unroll 1
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    const float jit = lvl == 0 ? 0.0f : (lvl == 1 ? 1e-6f : (lvl == 2 ? 1e-5f : 1e-4f));   // gpytorch psd_safe_cholesky ladder
+    tot = osc + sig2 + jit;
+    rho = osc / tot;
+    // ---- normalised Gram row -> tensor memory, 8 columns at a time (the "+ (1 - rho)" of the unit diagonal is added
+    //      when the row's pivot block is read).  rho k = 2^(log2 rho - |du|^2); padding rows / columns give exactly 0.
+    const float e0 = valid ? lg2a(rho) : -CUDART_INF_F;
+#pragma unroll 1
+    for (int g8 = 0; g8 < ngrp; ++g8) {
+      uint32_t g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 fb = lds4(&sf[8 * g8 + j][0]);
+        float e = e0;
+        { const float du = u[0] - fb.x; e = fmaf(-du, du, e); }
+        if (FT > 1) { const float du = u[1] - fb.y; e = fmaf(-du, du, e); }
+        if (FT > 2) { const float du = u[2] - fb.z; e = fmaf(-du, du, e); }
+        if (FT > 3) { const float du = u[3] - fb.w; e = fmaf(-du, du, e); }
+        g[j] = __float_as_uint(ex2a(e));
+      }
+      tmem_st8(lane_base + 8 * g8, g);
+    }
+    tmem_st_wait();
+    aug = r;
+    dadd = valid ? 1.0f - rho : 1.0f;
+    bool ok = true;
+    logdet2 = 0.0f;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    // ---- blocked symmetric Gauss-Jordan sweep, 4 pivots per block; the rank-4 update runs on the tensor cores
+#pragma unroll 1
+    for (int c = 0; c < nblk; ++c) {
+      if (c > 0) {
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        fence_after_sync();
+      }
+      float t0[4];
+      tmem_ld4(lane_base + 4 * c, t0);
+      const int rel = row - 4 * c;
+      const bool inb = (unsigned)rel < 4u;
+      {
+        float xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rel == j) t0[j] += dadd;                 // true diagonal
+          xv[j] = rel == j ? t0[j] - 1.0f : t0[j];     // X = T0 - I on the pivot block diagonal
+        }
+        *reinterpret_cast<float4*>(&s_t0[mtx][row][0]) = make_float4(t0[0], t0[1], t0[2], t0[3]);
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { hi[j] = tf32_hi(xv[j]); lo[j] = xv[j] - hi[j]; }
+        sts4(s_x_hi + ((row + mtx * kRows) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts4(s_x_lo + ((row + mtx * kRows) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
+        if (inb) s_aug[mtx][rel] = aug;
+      }
+      __syncthreads();
+      float B[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(&s_t0[mtx][4 * c + i][0]);
+        B[i][0] = v.x; B[i][1] = v.y; B[i][2] = v.z; B[i][3] = v.w;
+      }
+      const float4 augB = *reinterpret_cast<const float4*>(&s_aug[mtx][0]);
+      invert4_sym(B, ok, logdet2);
+      // negated multipliers nw = -w (Binv = -B): non-pivot rows w = t0 Binv, i.e. nw = t0 B
+      float nw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        nw[j] = fmaf(t0[3], PACOH_SYM(3, j), fmaf(t0[2], PACOH_SYM(2, j), fmaf(t0[1], PACOH_SYM(1, j), t0[0] * PACOH_SYM(0, j))));
+      if (inb) {   // pivot rows: B0[rel][:] Binv = e_rel exactly (no cond(B0) rounding), w = e_rel - Binv[rel][:]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float b01 = (rel & 1) ? PACOH_SYM(1, j) : PACOH_SYM(0, j), b23 = (rel & 1) ? PACOH_SYM(3, j) : PACOH_SYM(2, j);
+          const float brj = (rel & 2) ? b23 : b01;
+          nw[j] = (rel == j ? -1.0f : 0.0f) - brj;
+        }
+      }
+      aug = fmaf(nw[0], augB.x, fmaf(nw[1], augB.y, fmaf(nw[2], augB.z, fmaf(nw[3], augB.w, aug))));
+      {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { hi[j] = tf32_hi(nw[j]); lo[j] = nw[j] - hi[j]; }
+        sts4(s_w_hi + ((tid + mtx * kGT) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts4(s_w_lo + ((tid + mtx * kGT) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
+      }
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const uint64_t dwh = umma_desc(smem_u32(s_w_hi), kGT * 16, 128), dwl = umma_desc(smem_u32(s_w_lo), kGT * 16, 128);
+        const uint64_t dxh = umma_desc(smem_u32(s_x_hi), kRows * 16, 128), dxl = umma_desc(smem_u32(s_x_lo), kRows * 16, 128);
+        // D[128 x N] += W X^T : lo*hi, hi*lo, hi*hi
+        umma_tf32(tmem, dwl, dxh, idesc, 1);
+        umma_tf32(tmem, dwh, dxl, idesc, 1);
+        umma_tf32(tmem, dwh, dxh, idesc, 1);
+        umma_commit(bar);
+      }
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    fence_after_sync();
+    if (ok && status < 0) status = lvl;
+    const bool retry = !ok && lvl < 3 && pvalid;
+    if (retry) ++lvl;
+    if (!__syncthreads_or(retry ? 1 : 0)) break;     // both matrices done (or out of jitter levels)
+  }
+  if (!pvalid) status = 0;
+  const bool failed = status < 0;
+
+  // ---- gradient contraction over the row of -Khat^-1, read back from tensor memory 8 columns at a time:
+  //      w_ab = (beta_a alpha_hat_b - Khat^-1_ab) k_ab ; everything scaled at the end
+  sf[row][FT] = aug;
+  const float inv_tot = 1.0f / tot;
+  const float inv_n = 1.0f / (float)n;
+  const float beta = aug * inv_tot;
+  __syncthreads();
+  float S1[FT], Sk = 0.0f, dg = 0.0f;
+#pragma unroll
+  for (int f = 0; f < FT; ++f) S1[f] = 0.0f;
+#pragma unroll 1
+  for (int g8 = 0; g8 < ngrp; ++g8) {
+    float A[8];
+    tmem_ld8(lane_base + 8 * g8, A);
+    if ((row >> 3) == g8) {   // this row's diagonal entry: a select tree on the low 3 bits of the row index
+      const bool b0 = row & 1, b1 = row & 2, b2 = row & 4;
+      const float s0 = b0 ? A[1] : A[0], s1 = b0 ? A[3] : A[2], s2 = b0 ? A[5] : A[4], s3 = b0 ? A[7] : A[6];
+      const float t0 = b1 ? s1 : s0, t1 = b1 ? s3 : s2;
+      dg = b2 ? t1 : t0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 fb = lds4(&sf[8 * g8 + j][0]);
+      const float fbv[4] = {fb.x, fb.y, fb.z, fb.w};
+      float du[FT], e = 0.0f;
+#pragma unroll
+      for (int f = 0; f < FT; ++f) {
+        du[f] = u[f] - fbv[f];
+        e = fmaf(-du[f], du[f], e);
+      }
+      float alpha_b;
+      if (FT < 4) alpha_b = fbv[FT < 4 ? FT : 0];
+      else alpha_b = sf[8 * g8 + j][FT];
+      const float wv = fmaf(beta, alpha_b, A[j]) * ex2a(e);
+      Sk += wv;
+#pragma unroll
+      for (int f = 0; f < FT; ++f) S1[f] = fmaf(wv, du[f], S1[f]);
+    }
+  }
+  // ---- per-matrix sums over its two warps: quad, Sk, Str, dmean, S2[f]
+  //      sum_ab w_ab du_ab^2 = 2 sum_a u_a S1_a (w symmetric, du antisymmetric); sum_a S1_a = 0, so centre u on row 0
+  float red[4 + FT];
+  red[0] = warp_sum(r * aug);
+  red[1] = warp_sum(valid ? Sk : 0.0f);
+  red[2] = warp_sum(valid ? fmaf(beta, aug, dg - 1.0f - rho) : 0.0f);     // diagonal entries carry + (2 - dadd) = 1 + rho
+  red[3] = warp_sum(valid ? beta : 0.0f);
+#pragma unroll
+  for (int f = 0; f < FT; ++f) red[4 + f] = warp_sum(valid ? 2.0f * (u[f] - sf[0][f]) * S1[f] : 0.0f);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4 + FT; ++i) s_red[mtx][wim][i] = red[i];
+  }
+  __syncthreads();
+
+  if (pvalid) {
+    float* hyp = a.dhyp + ((size_t)p * a.T + t) * gp_hyp_stride(F);
+    if (valid) {
+      if (a.dmean != nullptr) a.dmean[q] = failed ? 0.0f : beta * inv_n;
+      if (a.dfeat != nullptr) {
+#pragma unroll
+        for (int f = 0; f < FT; ++f)
+          if (f < F) {
+            const float ls = softplus_f(__ldg(th + a.off_ls + f));
+            a.dfeat[q * F + f] = failed ? 0.0f : -rho * inv_n / (kC * ls) * S1[f];
+          }
+      }
+    }
+    if (row == 0) {
+      float* mll_out = a.mll + (size_t)p * a.T + t;
+      if (a.info != nullptr) a.info[(size_t)p * a.T + t] = status;
+      if (failed) {   // reference: gpytorch raises NotPSDError; the host wrapper does the same from `info`
+        *mll_out = CUDART_NAN_F;
+        for (int f = 0; f < F + 3; ++f) hyp[f] = 0.0f;
+      } else {
+        const float quad = (s_red[mtx][0][0] + s_red[mtx][1][0]) * inv_tot;
+        const float Skt = (s_red[mtx][0][1] + s_red[mtx][1][1]) - (float)n * (1.0f + rho);
+        const float Str = s_red[mtx][0][2] + s_red[mtx][1][2];
+        const float dms = (s_red[mtx][0][3] + s_red[mtx][1][3]) * inv_n;
+        const float logdet = (float)n * logf(tot) + logdet2 * 0.69314718055994530942f;
+        *mll_out = (-0.5f * quad - 0.5f * logdet - 0.5f * (float)n * 1.83787706640934548356f) * inv_n;
+#pragma unroll
+        for (int f = 0; f < FT; ++f)
+          if (f < F) {
+            // dL/dl_f = rho/(2 n) * S2 / (kC^2 l_f) ; chain through softplus
+            const float raw = __ldg(th + a.off_ls + f);
+            const float s2 = s_red[mtx][0][4 + f] + s_red[mtx][1][4 + f];
+            hyp[f] = 0.5f * rho * inv_n * s2 / (kC * kC * softplus_f(raw)) * sigmoid_f(raw);
+          }
+        hyp[F] = 0.5f * inv_tot * inv_n * Str * sigmoid_f(raw_noise);
+        hyp[F + 1] = a.has_oscale ? 0.5f * inv_tot * inv_n * Skt * sigmoid_f(raw_os) : 0.0f;
+        hyp[F + 2] = dms;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<kGpTmemCols>(tmem);
+}
+
+}  // namespace
+
+// Tensor-core GP kernel: 32 < n <= 64 and F <= 4 (FT + 4 reduction slots <= 8).
+int launch_gp_mll_tc(const GpArgs& a, cudaStream_t st) {
+  if (a.n <= 32 || a.n > 64 || a.F < 1 || a.F > 4) return PACOH_ERR_UNSUPPORTED;
+  const int pairs = a.P * a.T;
+  const int blocks = (pairs + 1) / 2;
+  if (a.F <= 2) gp_tc_kernel<2><<<blocks, kGT, 0, st>>>(a);
+  else gp_tc_kernel<4><<<blocks, kGT, 0, st>>>(a);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+}  // namespace pacoh

@@ -43,6 +43,7 @@ constexpr int kMaxGpN = 64;    // warp-per-matrix kernel: n <= 64
 constexpr int kMaxGpF = 16;    // feature dim
 __host__ __device__ inline int gp_hyp_stride(int F) { return F + 3; }
 int launch_gp_mll(const GpArgs& a, cudaStream_t st);
+int launch_gp_mll_tc(const GpArgs& a, cudaStream_t st);   // gp_tc.cu: tcgen05 / tensor-memory version, 32 < n <= 64, F <= 4
 
 // ---- reductions / elementwise (finalize.cu) ------------------------------------------------------------
 int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,

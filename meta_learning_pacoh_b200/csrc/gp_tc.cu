@@ -32,7 +32,7 @@ constexpr int kRows = 64;          // rows per matrix
 constexpr float kFar = 1.0e18f;    // scaled feature of a padding row: exp2(-(1e18)^2) == 0 exactly
 constexpr int kGpTmemCols = 64;
 #ifndef PACOH_GPTC_MINB
-#define PACOH_GPTC_MINB 6   // CTAs per SM the register allocation is capped for (tensor memory allows 8)
+#define PACOH_GPTC_MINB 8   // CTAs per SM the register allocation is capped for (tensor memory allows 8)
 #endif
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -93,16 +93,15 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
   __shared__ __align__(16) float s_aug[2][4];
   __shared__ __align__(16) float s_feat[2][kRows][RS];
   __shared__ float s_red[2][2][8];                                           // [matrix][warp-in-matrix][slot]
+  __shared__ float s_hyp[2][8][2];                                           // hyper-parameters, one per designated thread
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mtx = tid >> 6, row = tid & 63, wim = warp & 1;
-  const int pairs = a.P * a.T;
-  const int pair = blockIdx.x * 2 + mtx;
-  const bool pvalid = pair < pairs;
-  const int pr = pvalid ? pair : pairs - 1;
-  const int p = pr / a.T, t = pr - p * a.T;
+  const int p = blockIdx.y;                          // particle
+  const bool pvalid = blockIdx.x * 2 + mtx < a.T;    // odd T: the last CTA's second matrix is a dummy
+  const int t = pvalid ? blockIdx.x * 2 + mtx : a.T - 1;
   const int n = a.n, F = a.F, Q = a.T * a.n;
   const int src = __ldg(a.task_idx + t);
   const float* th = a.theta + (size_t)p * a.D;
@@ -115,11 +114,29 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
   sts4(s_w_lo + ((tid + (1 - mtx) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
 
   // ---- hyper-parameters (random_gp.py:69-73; MAP: GPR_meta_mll.py:54-55,218)
+  //      computed once per matrix: rows 0..FT-1 take a lengthscale each, row 4 the noise, row 5 the output scale;
+  //      slot [.][0] = the value the sweep needs, slot [.][1] = the softplus chain factor of its gradient
   const float kC = 0.84932180028801904272f;   // sqrt(0.5 * log2(e))
-  const float raw_noise = __ldg(th + a.off_noise);
-  const float sig2 = a.noise_floor + softplus_f(raw_noise);
-  const float raw_os = a.has_oscale ? __ldg(th + a.off_oscale) : 0.0f;
-  const float osc = a.has_oscale ? softplus_f(raw_os) : 1.0f;
+  if (row < 6) {
+    float v0 = 0.0f, v1 = 0.0f;
+    if (row < FT) {
+      if (row < F) {
+        const float raw = __ldg(th + a.off_ls + row), ls = softplus_f(raw);
+        v0 = kC / ls;                                  // scaled inverse lengthscale
+        v1 = 0.5f * sigmoid_f(raw) / (kC * kC * ls);   // dL/dl_f = rho/(2 n) * S2 / (kC^2 l_f) ; chain through softplus
+      }
+    } else if (row == 4) {
+      const float raw = __ldg(th + a.off_noise);
+      v0 = a.noise_floor + softplus_f(raw);
+      v1 = sigmoid_f(raw);
+    } else if (row == 5) {
+      const float raw = a.has_oscale ? __ldg(th + a.off_oscale) : 0.0f;
+      v0 = a.has_oscale ? softplus_f(raw) : 1.0f;
+      v1 = a.has_oscale ? sigmoid_f(raw) : 0.0f;
+    }
+    s_hyp[mtx][row][0] = v0;
+    s_hyp[mtx][row][1] = v1;
+  }
 
   // ---- this thread's row: residual and scaled features (padding rows sit "infinitely far" away => zero Gram rows)
   const bool valid = row < n;
@@ -131,17 +148,19 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
     r = valid ? __ldg(a.y + (size_t)src * n + row) - m : 0.0f;
 #pragma unroll
     for (int f = 0; f < FT; ++f) {
-      float z = 0.0f;
-      if (valid && f < F) z = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * n + row) * a.d + f);
-      const float inv_ls = f < F ? kC / softplus_f(__ldg(th + a.off_ls + f)) : 0.0f;
-      u[f] = valid ? z * inv_ls : kFar;
+      u[f] = 0.0f;
+      if (valid && f < F) u[f] = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * n + row) * a.d + f);
     }
-#pragma unroll
-    for (int f = 0; f < RS; ++f) sf[row][f] = f < FT ? u[f] : 0.0f;
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  const float sig2 = s_hyp[mtx][4][0], osc = s_hyp[mtx][5][0];
+#pragma unroll
+  for (int f = 0; f < FT; ++f) u[f] = valid ? u[f] * s_hyp[mtx][f][0] : kFar;
+#pragma unroll
+  for (int f = 0; f < RS; ++f) sf[row][f] = f < FT ? u[f] : 0.0f;
+  __syncthreads();
   const uint32_t tmem = tmem_base_s;
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t bar = smem_u32(&mbar);
@@ -187,7 +206,7 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
 #pragma unroll 1
     for (int c = 0; c < nblk; ++c) {
       if (c > 0) {
-        mbar_wait(bar, parity);
+        mbar_wait_hint(bar, parity, 2000u);
         parity ^= 1;
         fence_after_sync();
       }
@@ -254,7 +273,7 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
         umma_commit(bar);
       }
     }
-    mbar_wait(bar, parity);
+    mbar_wait_hint(bar, parity, 2000u);
     parity ^= 1;
     fence_after_sync();
     if (ok && status < 0) status = lvl;
@@ -326,10 +345,7 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
       if (a.dfeat != nullptr) {
 #pragma unroll
         for (int f = 0; f < FT; ++f)
-          if (f < F) {
-            const float ls = softplus_f(__ldg(th + a.off_ls + f));
-            a.dfeat[q * F + f] = failed ? 0.0f : -rho * inv_n / (kC * ls) * S1[f];
-          }
+          if (f < F) a.dfeat[q * F + f] = failed ? 0.0f : -rho * inv_n * s_hyp[mtx][f][0] / (kC * kC) * S1[f];
       }
     }
     if (row == 0) {
@@ -347,14 +363,9 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
         *mll_out = (-0.5f * quad - 0.5f * logdet - 0.5f * (float)n * 1.83787706640934548356f) * inv_n;
 #pragma unroll
         for (int f = 0; f < FT; ++f)
-          if (f < F) {
-            // dL/dl_f = rho/(2 n) * S2 / (kC^2 l_f) ; chain through softplus
-            const float raw = __ldg(th + a.off_ls + f);
-            const float s2 = s_red[mtx][0][4 + f] + s_red[mtx][1][4 + f];
-            hyp[f] = 0.5f * rho * inv_n * s2 / (kC * kC * softplus_f(raw)) * sigmoid_f(raw);
-          }
-        hyp[F] = 0.5f * inv_tot * inv_n * Str * sigmoid_f(raw_noise);
-        hyp[F + 1] = a.has_oscale ? 0.5f * inv_tot * inv_n * Skt * sigmoid_f(raw_os) : 0.0f;
+          if (f < F) hyp[f] = rho * inv_n * (s_red[mtx][0][4 + f] + s_red[mtx][1][4 + f]) * s_hyp[mtx][f][1];
+        hyp[F] = 0.5f * inv_tot * inv_n * Str * s_hyp[mtx][4][1];
+        hyp[F + 1] = 0.5f * inv_tot * inv_n * Skt * s_hyp[mtx][5][1];
         hyp[F + 2] = dms;
       }
     }
@@ -369,10 +380,16 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
 // Tensor-core GP kernel: 32 < n <= 64 and F <= 4 (FT + 4 reduction slots <= 8).
 int launch_gp_mll_tc(const GpArgs& a, cudaStream_t st) {
   if (a.n <= 32 || a.n > 64 || a.F < 1 || a.F > 4) return PACOH_ERR_UNSUPPORTED;
-  const int pairs = a.P * a.T;
-  const int blocks = (pairs + 1) / 2;
-  if (a.F <= 2) gp_tc_kernel<2><<<blocks, kGT, 0, st>>>(a);
-  else gp_tc_kernel<4><<<blocks, kGT, 0, st>>>(a);
+  if (a.P > 65535) return PACOH_ERR_UNSUPPORTED;
+  static bool carveout_set = false;
+  if (!carveout_set) {   // 8 CTAs / SM need 8 x 17 KB of shared memory: ask for the large carve-out (L1 is not used)
+    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
+  const dim3 grid((a.T + 1) / 2, a.P);
+  if (a.F <= 2) gp_tc_kernel<2><<<grid, kGT, 0, st>>>(a);
+  else gp_tc_kernel<4><<<grid, kGT, 0, st>>>(a);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

@@ -84,12 +84,23 @@ static int sm_count() {
   return sms;
 }
 
-// Number of tile chunks (CTAs per particle per net) of the MLP kernels: ~16 waves of CTAs, >= 4 tiles per warp.
-static int mlp_chunks(int P, int nets, int Q) {
+// Number of tile chunks (CTAs per particle per net) of the MLP kernels: the count with the least wave-quantisation
+// loss, fixed per-CTA cost (weight staging, TMEM allocation, final reduction ~ one tile round) included.
+//   backward: ONE 3-warpgroup CTA per SM, each warpgroup walks every third tile of its chunk (the chunk count also
+//             sizes the per-chunk gradient partials);  forward: 4 CTAs per SM, one tile at a time.
+static int mlp_chunks(int P, int nets, int Q, bool bwd) {
   const int tiles = (Q + kTileP - 1) / kTileP;
-  int by_waves = (sm_count() * 16 + P * nets - 1) / (P * nets);
-  int by_work = (tiles + 31) / 32;
-  return std::max(1, std::min(by_waves, by_work));
+  const long long slots = (long long)sm_count() * (bwd ? 1 : 4), ctas = (long long)P * nets;
+  const int cmax = std::max(1, std::min(tiles / 8, 256));
+  int best = 1;
+  long long best_cost = -1;
+  for (int c = 1; c <= cmax; ++c) {
+    const long long per = (tiles + c - 1) / c;
+    const long long rounds = bwd ? (per + 2) / 3 + 1 : per + 2;
+    const long long cost = ((ctas * c + slots - 1) / slots) * rounds;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
 // The MLP forward runs on the tensor cores (mlp_tc.cu, 3xTF32 tcgen05) unless PACOH_MLP_FWD=ffma selects the
@@ -119,7 +130,7 @@ static int launch_mlp_best(const MlpArgs& ma, int nets, int chunks, bool bwd, cu
 
 struct Plan {
   ModelDev m;
-  int Q, chunks;
+  int Q, chunks, chunks_fwd;   // chunks: backward kernels (sizes the gradient partials); chunks_fwd: forward kernels
   bool mean_nn, kern_nn, mean_fast, kern_fast, fused;   // fused: one launch covers both nets
   size_t off_mean, off_feat, off_dmean, off_dfeat, off_mll, off_hyp, off_pmean, off_pkern, off_gen, total;
 };
@@ -138,7 +149,8 @@ static int make_plan(const pacoh_arch_t* arch, int P, int T, int n, Plan* pl) {
   pl->mean_fast = pl->mean_nn && net_is_fast(m.mean, m.d);
   pl->kern_fast = pl->kern_nn && net_is_fast(m.kern, m.d);
   pl->fused = pl->mean_fast && pl->kern_fast && m.mean.n_hidden == m.kern.n_hidden;
-  pl->chunks = mlp_chunks(P, pl->fused ? 2 : 1, pl->Q);
+  pl->chunks = mlp_chunks(P, pl->fused ? 2 : 1, pl->Q, true);
+  pl->chunks_fwd = mlp_chunks(P, pl->fused ? 2 : 1, pl->Q, false);
   const size_t PQ = (size_t)P * pl->Q;
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats); return o; };
@@ -288,7 +300,7 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
       ma.out[0] = ws + pl.off_mean; ma.out[1] = ws + pl.off_feat;
       ma.dout[0] = ws + pl.off_dmean; ma.dout[1] = ws + pl.off_dfeat;
       ma.partial[0] = ws + pl.off_pmean; ma.partial[1] = ws + pl.off_pkern;
-      return launch_mlp_best(ma, 2, pl.chunks, bwd, st);
+      return launch_mlp_best(ma, 2, bwd ? pl.chunks : pl.chunks_fwd, bwd, st);
     }
     for (int z = 0; z < 2; ++z) {
       const bool is_nn = z == 0 ? pl.mean_nn : pl.kern_nn;
@@ -298,7 +310,7 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
       ma.dout[0] = ws + (z == 0 ? pl.off_dmean : pl.off_dfeat);
       ma.partial[0] = ws + (z == 0 ? pl.off_pmean : pl.off_pkern);
       const bool fast = z == 0 ? pl.mean_fast : pl.kern_fast;
-      int r = fast ? launch_mlp_best(ma, 1, pl.chunks, bwd, st)
+      int r = fast ? launch_mlp_best(ma, 1, bwd ? pl.chunks : pl.chunks_fwd, bwd, st)
                    : launch_mlp_generic(ma, 0, pl.chunks, bwd, ws + pl.off_gen, st);
       if (r != PACOH_OK) return r;
     }
@@ -359,7 +371,7 @@ extern "C" int pacoh_gp_forward(const pacoh_arch_t* arch, int32_t P, int32_t npt
   memset(&ma, 0, sizeof(ma));
   ma.theta = theta; ma.x = x; ma.task_idx = nullptr;
   ma.P = P; ma.T = 1; ma.n = npts; ma.d = m.d; ma.D = m.D;
-  const int chunks = mlp_chunks(P, 1, npts);
+  const int chunks = mlp_chunks(P, 1, npts, false);
   for (int z = 0; z < 2; ++z) {
     const bool is_nn = z == 0 ? pl.mean_nn : pl.kern_nn;
     float* dst = z == 0 ? mean : feat;

@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(MlpArgs a) {
 
   const int Q = a.T * a.n;
   const int tiles = (Q + kTileP - 1) / kTileP;
-  const int per = (tiles + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = min(tiles, t0 + per);
+  // balanced split: chunk sizes differ by at most one tile
+  const int t0 = (int)(((long long)tiles * blockIdx.x) / gridDim.x), t1 = (int)(((long long)tiles * (blockIdx.x + 1)) / gridDim.x);
   float* outp = a.out[blockIdx.z] + (size_t)p * Q * net.out_dim;
 
   for (int tile = t0 + warp; tile < t1; tile += kWarps) {
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(MlpArgs a) {
 
   const int Q = a.T * a.n;
   const int tiles = (Q + kTileP - 1) / kTileP;
-  const int per = (tiles + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = min(tiles, t0 + per);
+  // balanced split: chunk sizes differ by at most one tile
+  const int t0 = (int)(((long long)tiles * blockIdx.x) / gridDim.x), t1 = (int)(((long long)tiles * (blockIdx.x + 1)) / gridDim.x);
 
   // persistent per-lane accumulators (partial sums over this warp's tiles)
   constexpr int LH = L > 1 ? L - 1 : 1;

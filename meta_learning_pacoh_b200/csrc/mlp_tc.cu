@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
 
   const int Q = a.T * a.n;
   const int tiles = (Q + kTcTile - 1) / kTcTile;
-  const int per = (tiles + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = min(tiles, t0 + per);
+  // balanced split: chunk sizes differ by at most one tile
+  const int t0 = (int)(((long long)tiles * blockIdx.x) / gridDim.x), t1 = (int)(((long long)tiles * (blockIdx.x + 1)) / gridDim.x);
   float* outp = a.out[blockIdx.z] + (size_t)p * Q * net.out_dim;
 
   // inputs of the NEXT tile are loaded one tile ahead (global latency hidden behind the current tile)

@@ -1,17 +1,27 @@
 // Tensor-core backward pass of the per-particle MLPs (recompute-forward + reverse pass), sm_100a.
 //
 // Same semantics as mlp_bwd_kernel in mlp.cu (the autograd reverse pass through NeuralNetworkVectorized,
-// meta_learn/models.py:295-317, 343-349, svgd.py:16).  Work split per 128-point tile (thread t owns point t):
+// meta_learn/models.py:295-317, 343-349, svgd.py:16).  One CTA = THREE independent warpgroups that share the staged
+// weights; each warpgroup walks its own 128-point tiles (thread t owns point t) with its own tensor-memory columns,
+// mbarriers and named barrier, so the three tile pipelines hide each other's MMA / barrier round trips.
 //
-//   tensor cores (tcgen05, 3xTF32, A and D in TMEM)    CUDA cores
-//   -------------------------------------------          -----------------------------------------------------------------
-//   H_l   = tanh(H_{l-1} W_l^T + b_l)   (recompute)      layer 1, tanh, hi/lo splitting, output-layer backward
-//   dH_{l-1} = dA_l W_l                                  dW_l += dA_l^T H_{l-1}  as a 32x32x32 warp GEMM over the warp's own 32
-//                                                        points -- issued while the dH MMA of the same layer is in flight
+//   tensor cores (tcgen05, 3xTF32, accumulators in TMEM)             CUDA cores
+//   ------------------------------------------------------------     ------------------------------------------------
+//   H_l      = tanh(H_{l-1} W_l^T + b_l)  (recompute; A in TMEM)     layer 1, tanh, hi/lo splitting, output-layer backward,
+//   dH_{l-1} = dA_l W_l                   (A in TMEM)                bias / first-layer / output-layer gradients as
+//   dW_l    += dA_l^T H_{l-1}             (both operands in smem,    lane-per-feature row sums
+//              K = the 128 points of the tile; the accumulator
+//              stays in tensor memory over ALL tiles of the warpgroup)
 //
-// Every hidden layer keeps one per-warp [feature][point] tile (first H_l^T, later overwritten in place by dA_l^T); the
-// bias / first-layer / output-layer gradients are lane-per-feature row sums over those tiles.  Accumulators persist in
-// registers over all tiles of the CTA and are reduced once, in a fixed order, into a (chunk, particle) partial.
+// The weight-gradient GEMM needs its operands K-major with K = points, i.e. TRANSPOSED tiles [feature][point].  Each
+// thread writes its point's column of dA_l^T / H_{l-1}^T straight into a SWIZZLE_128B K-major tile: a warp's 32 points
+// are one 128-byte swizzle row per feature (conflict-free column stores AND conflict-free lane-per-feature row reads),
+// one 8 KB K-block per warp.  The lo parts are STACKED under the values along M / N (rows 0-31: the unsplit fp32
+// value -- the tensor core truncates it to tf32 itself --, rows 32-63: value - tf32(value)), so ONE M128 N64 MMA per
+// 8 points yields hi*hi, hi*lo and lo*hi as separate 32x32 blocks of the accumulator (summed once per CTA):
+// 16 MMAs per tile instead of 48.  (Layout and truncation validated by tools/ubench/tc_sw128_test.cu.)
+// The dW MMAs are issued by a second thread and committed to their own mbarrier, so they overlap the dH round trip;
+// the operand tiles are only waited for right before they are overwritten.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -22,51 +32,72 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 128;
-constexpr int kWarps = 4;
+constexpr int kWG = 3;                   // warpgroups (independent tile pipelines) per CTA
+constexpr int kWGThreads = 128;
+constexpr int kThreads = kWG * kWGThreads;
+constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 128;
-constexpr int kTF = kHid * kSRow;   // floats of one per-warp [32 features][36] tile
+constexpr int kStackF = 8192;            // floats of one stacked transposed tile [64 rows][128 points] (32 KB)
+// tensor-memory columns of one warpgroup: D 32 | A hi 32 | A lo 32 (tc_common.cuh) | dW accumulator 64
+constexpr uint32_t kTmemDW = 96;
+constexpr uint32_t kTmemWG = 160;
+
+// K-major SWIZZLE_128B shared-memory descriptor: 8-row groups 1024 B apart, start address may advance by 32 B per K-step
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;      // stride byte offset
+  d |= (uint64_t)1 << 46;                // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+  return d;
+}
 
 template <int L, int DIN, int OUT>
 struct BwdSmem {
-  static constexpr int B = 0;                                      // per layer l = 2..L: W hi, W lo, W^T hi, W^T lo (1024 floats each)
-  static constexpr int W1 = B + (L - 1) * 4 * kHid * kHid;         // [32][DIN]
+  static constexpr int LH = L > 1 ? L - 1 : 0;
+  // per-warpgroup stacked transposed tiles first (1024-byte aligned; the M = 128 MMA over-reads the 64-row dA^T tile
+  // by 8 row groups: that stays inside the warpgroup's H^T tile / the next warpgroup's tiles / the weights)
+  static constexpr int WG_TILES = (1 + LH) * kStackF;              // dA_l^T, then H_l^T for l = 1..L-1
+  static constexpr int B = kWG * WG_TILES;                         // per layer l = 2..L: W hi, W lo, W^T hi, W^T lo (1024 floats each)
+  static constexpr int W1 = B + (LH > 0 ? LH : 1) * 4 * kHid * kHid;   // [32][DIN]
   static constexpr int B1 = W1 + kHid * DIN;
   static constexpr int BH = B1 + kHid;                             // biases of layers 2..L
-  static constexpr int WOUT = BH + (L - 1) * kHid;                 // [OUT][32]
+  static constexpr int WOUT = BH + LH * kHid;                      // [OUT][32]
   static constexpr int BOUT = WOUT + OUT * kHid;
   static constexpr int WARP = BOUT + 4;
   // per-warp region
-  static constexpr int T = 0;                                      // L tiles [32][36]: H_l^T, later dA_l^T
-  static constexpr int X = T + L * kTF;                            // [DIN][32]
+  static constexpr int X = 0;                                      // [DIN][32]
   static constexpr int DOUT = X + DIN * 32;                        // [OUT][32]
   static constexpr int WARP_SIZE = DOUT + 4 * ((OUT * 32 + 3) / 4);
   static constexpr int END = WARP + kWarps * WARP_SIZE;
-  // padded accumulator layout for the in-CTA reduction (aliases the per-warp regions): b1, W1, (b_l, W_l) l = 2..L, bout, Wout
+  // padded accumulator layout for the in-CTA reduction (aliases warpgroup 0's tiles): b1, W1, (b_l, W_l) l = 2..L, bout, Wout
   static constexpr int R_B1 = 0;
   static constexpr int R_W1 = kHid;
   static constexpr int R_H = R_W1 + kHid * DIN;
   static constexpr int R_HSTRIDE = kHid + kHid * kHid;
-  static constexpr int R_BO = R_H + (L - 1) * R_HSTRIDE;
+  static constexpr int R_BO = R_H + LH * R_HSTRIDE;
   static constexpr int R_WO = R_BO + OUT;
   static constexpr int R_END = R_WO + OUT * kHid;
-  static_assert(R_END <= kWarps * WARP_SIZE, "reduction buffer must fit in the per-warp regions");
+  static_assert(R_END <= kStackF, "reduction buffer must fit in one stacked tile");
+  static_assert(L <= 2, "deeper nets do not fit three warpgroups of transposed tiles in shared memory");
 };
 
 template <int L, int DIN, int OUT>
-__global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   using S = BwdSmem<L, DIN, OUT>;
   extern __shared__ __align__(1024) float smem[];
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[kWG][2];
   __shared__ uint32_t tmem_base_s;
   const NetDev& net = a.net[blockIdx.z];
   const int p = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = tid >> 7, wt = tid & 127, wq = warp & 3;      // warpgroup, thread / warp inside it
   const float* th = a.theta + (size_t)p * a.D;
-  float* sw = smem + S::WARP + warp * S::WARP_SIZE;   // this warp's region
+  float* sw = smem + S::WARP + warp * S::WARP_SIZE;             // this warp's region
 
-  if (warp == 0) tmem_alloc<kTmemCols>(&tmem_base_s);
-  if (tid == 0) mbar_init(smem_u32(&mbar), 1);
-  // ---- stage the particle's weights
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  if (tid < kWG) { mbar_init(smem_u32(&mbar[tid][0]), 1); mbar_init(smem_u32(&mbar[tid][1]), 1); }
+  // ---- stage the particle's weights (shared by the three warpgroups)
   const int w0 = net.width[0];
   for (int i = tid; i < kHid * DIN; i += kThreads) {
     const int j = i / DIN, dd = i - j * DIN;
@@ -98,24 +129,27 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
-  const uint32_t bar = smem_u32(&mbar);
-  uint32_t parity = 0;
+  const uint32_t tmem = tmem_base_s + kTmemWG * wg;                    // this warpgroup's columns
+  const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);       // this warp's 32 TMEM lanes
+  const uint32_t bar = smem_u32(&mbar[wg][0]), bar_dw = smem_u32(&mbar[wg][1]);
+  uint32_t parity = 0, parity_dw = 0;
+  bool dw_pending = false;     // dW MMAs in flight still read the transposed tiles
+  auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory"); };
+  // ---- zero the dW accumulator (it is only ever accumulated into)
+  if (L > 1) {
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_st16(lane_base + kTmemDW + 16 * c, z);
+    tmem_st_wait();
+  }
 
   // ---- persistent accumulators
-  constexpr int LH = L > 1 ? L - 1 : 1;
-  float accW[LH][8][4];    // dW_l[j = jb + 4e][k = kb + 8f], jb = lane >> 3, kb = lane & 7 (this warp's points)
   float accb[L];           // db_l[lane]
   float accWo[OUT];        // dWout[o][lane]
   float accbo[OUT];        // dbout[o], per-thread partial over its own points
   float accW1[DIN];        // dW1[lane][dd]
-#pragma unroll
-  for (int l = 0; l < LH; ++l)
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-#pragma unroll
-      for (int f = 0; f < 4; ++f) accW[l][e][f] = 0.0f;
 #pragma unroll
   for (int l = 0; l < L; ++l) accb[l] = 0.0f;
 #pragma unroll
@@ -125,12 +159,12 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
 
   const int Q = a.T * a.n;
   const int tiles = (Q + kTile - 1) / kTile;
-  const int per = (tiles + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = min(tiles, t0 + per);
+  // balanced split: chunk sizes differ by at most one tile; inside the CTA the warpgroups interleave
+  const int t0 = (int)(((long long)tiles * blockIdx.x) / gridDim.x), t1 = (int)(((long long)tiles * (blockIdx.x + 1)) / gridDim.x);
 
   // this point's inputs / output gradients; the loads for the NEXT tile are issued one tile ahead (latency hidden)
   auto load_point = [&](int tile_i, float (&xo)[DIN], float (&dro)[OUT]) {
-    const int qq = tile_i * kTile + tid;
+    const int qq = tile_i * kTile + wt;
     const bool ok = tile_i < t1 && qq < Q;
     int src = 0;
     if (ok) {
@@ -144,9 +178,35 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
     for (int o = 0; o < OUT; ++o) dro[o] = (ok && o < net.out_dim) ? __ldg(dsrc + o) : 0.0f;
   };
   float xn[DIN], drn[OUT];
-  load_point(t0, xn, drn);
+  load_point(t0 + wg, xn, drn);
 
-  for (int tile = t0; tile < t1; ++tile) {
+  // ---- addressing of the stacked SWIZZLE_128B tiles.  Row r, this warp's K-block, point = lane:
+  //      float offset = wq * 2048 + (r >> 3) * 256 + (r & 7) * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)
+  float* AT = smem + wg * S::WG_TILES;               // dA_l^T stack (values rows 0-31, lo rows 32-63)
+  float* kblk = AT + wq * 2048;                      // this warp's K-block of the dA^T stack
+  int xo[8];                                         // swizzled position of this point inside row (r & 7) == j
+#pragma unroll
+  for (int j = 0; j < 8; ++j) xo[j] = (((lane >> 2) ^ j) << 2) + (lane & 3);
+  const int rrow = (lane >> 3) * 256 + (lane & 7) * 32;   // row `lane` (lane-per-feature reads)
+  const int rsw = (lane & 7) << 2;                        // its swizzle: logical chunk c sits at float offset ((4 c) ^ rsw)
+  // this point's column -> rows 0-31 (value) and 32-63 (lo) of a stacked tile's K-block
+  auto publish_col = [&](float* kb, const float (&v)[kHid]) {
+#pragma unroll
+    for (int f = 0; f < kHid; ++f) {
+      const int o = (f >> 3) * 256 + (f & 7) * 32 + xo[f & 7];
+      kb[o] = v[f];
+      kb[o + 1024] = v[f] - tf32_hi(v[f]);
+    }
+  };
+  auto wait_dw = [&]() {
+    if (dw_pending) {
+      mbar_wait(bar_dw, parity_dw);
+      parity_dw ^= 1;
+      dw_pending = false;
+    }
+  };
+
+  for (int tile = t0 + wg; tile < t1; tile += kWG) {
     float x[DIN], dr[OUT];
 #pragma unroll
     for (int dd = 0; dd < DIN; ++dd) {
@@ -159,8 +219,8 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
       sw[S::DOUT + o * 32 + lane] = dr[o];
       accbo[o] += dr[o];
     }
-    load_point(tile + 1, xn, drn);
-    // ---- forward recompute: layer 1 in registers, layers 2..L on the tensor cores; H_l^T kept in the warp tiles
+    load_point(tile + kWG, xn, drn);
+    // ---- forward recompute: layer 1 in registers, layers 2..L on the tensor cores; H_l^T kept in the transposed tiles
     float h[kHid];
 #pragma unroll
     for (int j4 = 0; j4 < kHid; j4 += 4) {
@@ -173,15 +233,14 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
         h[j4 + e] = tanh_fast(acc[e]);
       }
     }
+    wait_dw();                                      // the previous tile's dW MMAs are done with the transposed tiles
 #pragma unroll
     for (int l = 2; l <= L; ++l) {
-      float* Tprev = sw + S::T + (l - 2) * kTF;
-#pragma unroll
-      for (int k = 0; k < kHid; ++k) Tprev[k * kSRow + lane] = h[k];
+      publish_col(kblk + (l - 1) * kStackF, h);     // H_{l-1}^T
       store_a_tmem(lane_base, h);                   // A operand of the recompute GEMM: this point's row -> its TMEM lane
       fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      wg_sync();
+      if (wt == 0) {
         fence_after_sync();
         const uint32_t b_hi = smem_u32(smem + S::B + (l - 2) * 4 * kHid * kHid);
         gemm128x32x32_3xtf32_ts(tmem, b_hi, b_hi + kHid * kHid * 4, bar);
@@ -200,17 +259,17 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
         h[j4 + 3] = tanh_fast(__uint_as_float(v[j4 + 3]) + b.w);
       }
     }
-    // ---- output layer backward.  dWout[o][j] += sum_pt H_L[pt][j] dout[pt][o] as a lane-per-feature row sum
-    float* TL = sw + S::T + (L - 1) * kTF;
+    // ---- output layer backward.  dWout[o][j] += sum_pt H_L[pt][j] dout[pt][o] as a lane-per-feature row sum over
+    //      H_L^T, parked in the value rows of this warp's (idle) dA^T K-block
 #pragma unroll
-    for (int k = 0; k < kHid; ++k) TL[k * kSRow + lane] = h[k];
+    for (int f = 0; f < kHid; ++f) kblk[(f >> 3) * 256 + (f & 7) * 32 + xo[f & 7]] = h[f];
     __syncwarp();
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 hv = lds4(TL + lane * kSRow + 4 * g);
+    for (int c = 0; c < 8; ++c) {
+      const float4 hv = lds4(kblk + rrow + ((4 * c) ^ rsw));
 #pragma unroll
       for (int o = 0; o < OUT; ++o) {
-        const float4 dv = lds4(sw + S::DOUT + o * 32 + 4 * g);
+        const float4 dv = lds4(sw + S::DOUT + o * 32 + 4 * c);
         accWo[o] += fmaf(hv.x, dv.x, fmaf(hv.y, dv.y, fmaf(hv.z, dv.z, hv.w * dv.w)));
       }
     }
@@ -226,44 +285,39 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) da[j4 + e] = dh[e] * fmaf(-h[j4 + e], h[j4 + e], 1.0f);
     }
+    __syncwarp();                                   // every lane is done with the H_L^T row sums
     // ---- hidden layers L..2
 #pragma unroll
     for (int l = L; l >= 2; --l) {
-      float* Tl = sw + S::T + (l - 1) * kTF;        // H_l^T  -> dA_l^T
-      float* Tp = sw + S::T + (l - 2) * kTF;        // H_{l-1}^T
-      __syncwarp();                                 // every lane is done reading H_l^T
-#pragma unroll
-      for (int k = 0; k < kHid; ++k) Tl[k * kSRow + lane] = da[k];
+      float* HTk = kblk + (l - 1) * kStackF;        // this warp's K-block of the H_{l-1}^T stack
+      wait_dw();
+      publish_col(kblk, da);                        // dA_l^T
       store_a_tmem(lane_base, da);
+      fence_async_smem();                           // transposed tiles (generic-proxy stores) -> visible to the MMA
       fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      wg_sync();
+      if (wt == 0) {
         fence_after_sync();
         const uint32_t bt_hi = smem_u32(smem + S::B + (l - 2) * 4 * kHid * kHid + 2 * kHid * kHid);
         gemm128x32x32_3xtf32_ts(tmem, bt_hi, bt_hi + kHid * kHid * 4, bar);              // dH_{l-1} = dA_l W_l
+      } else if (wt == 32) {                        // a second issuer: the weight-gradient GEMM, on its own barrier
+        fence_after_sync();
+        const uint32_t idesc = umma_idesc_tf32(128, 64);
+        const uint64_t da0 = umma_desc_sw128(smem_u32(AT)), db0 = umma_desc_sw128(smem_u32(AT + (l - 1) * kStackF));
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)            // 8 points = 32 B inside the 128-byte swizzle row; K-block = 8 KB
+            umma_tf32(tmem + kTmemDW, da0 + (uint64_t)(w * 512 + ks * 2), db0 + (uint64_t)(w * 512 + ks * 2), idesc, 1);
+        umma_commit(bar_dw);
       }
-      // ---- while the MMA runs: dW_l += dA_l^T H_{l-1} over this warp's 32 points, and db_l
+      dw_pending = true;
+      // ---- while the MMAs run: db_l[lane] = row sum of dA_l^T over this warp's points
       {
-        const int jb = lane >> 3, kb = lane & 7;
-        const float* sA = Tl + jb * kSRow;
-        const float* sB = Tp + kb * kSRow;
-#pragma unroll 2
-        for (int g = 0; g < 8; ++g) {
-          float4 bv[4];
-#pragma unroll
-          for (int f = 0; f < 4; ++f) bv[f] = lds4(sB + 8 * f * kSRow + 4 * g);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 av = lds4(sA + 4 * e * kSRow + 4 * g);
-#pragma unroll
-            for (int f = 0; f < 4; ++f)
-              accW[l - 2][e][f] += fmaf(av.x, bv[f].x, fmaf(av.y, bv[f].y, fmaf(av.z, bv[f].z, av.w * bv[f].w)));
-          }
-        }
         float s = 0.0f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 v4 = lds4(Tl + lane * kSRow + 4 * g);
+        for (int c = 0; c < 8; ++c) {
+          const float4 v4 = lds4(kblk + rrow + ((4 * c) ^ rsw));   // swizzled order: conflict-free, and a sum does not care
           s += (v4.x + v4.y) + (v4.z + v4.w);
         }
         accb[l - 1] += s;
@@ -273,55 +327,61 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
       fence_after_sync();
       uint32_t v[32];
       tmem_ld32(lane_base + kTmemD, v);
-      __syncwarp();                                 // the warp GEMM above is done reading H_{l-1}^T
 #pragma unroll
       for (int k = 0; k < kHid; ++k) {
-        const float hp = Tp[k * kSRow + lane];
+        const float hp = HTk[(k >> 3) * 256 + (k & 7) * 32 + xo[k & 7]];
         da[k] = __uint_as_float(v[k]) * fmaf(-hp, hp, 1.0f);
       }
     }
-    // ---- first layer: db1, dW1 as lane-per-feature row sums over dA_1^T
+    // ---- first layer: db1, dW1 as lane-per-feature row sums over dA_1^T (parked in the dA^T K-block again)
     {
-      float* T1 = sw + S::T;
-      __syncwarp();
+      wait_dw();                                    // the dW MMAs are done reading the dA^T stack
 #pragma unroll
-      for (int k = 0; k < kHid; ++k) T1[k * kSRow + lane] = da[k];
+      for (int f = 0; f < kHid; ++f) kblk[(f >> 3) * 256 + (f & 7) * 32 + xo[f & 7]] = da[f];
       __syncwarp();
       float s = 0.0f;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 v4 = lds4(T1 + lane * kSRow + 4 * g);
+      for (int c = 0; c < 8; ++c) {
+        const float4 v4 = lds4(kblk + rrow + ((4 * c) ^ rsw));
         s += (v4.x + v4.y) + (v4.z + v4.w);
 #pragma unroll
         for (int dd = 0; dd < DIN; ++dd) {
-          const float4 xv = lds4(sw + S::X + dd * 32 + 4 * g);
+          const float4 xv = lds4(sw + S::X + dd * 32 + 4 * c);
           accW1[dd] += fmaf(v4.x, xv.x, fmaf(v4.y, xv.y, fmaf(v4.z, xv.z, v4.w * xv.w)));
         }
       }
       accb[0] += s;
-      __syncwarp();                                 // before the next tile overwrites X / DOUT / T
+      __syncwarp();                                 // before the next tile overwrites X / DOUT / the K-block
     }
   }
 
-  // ---- reduce: warps in a fixed order into the padded layout (aliasing the A tiles), then un-pad to the flat order
+  // ---- reduce: warps in a fixed order into the padded layout (aliasing warpgroup 0's tiles), then un-pad to the flat order
+  wait_dw();
+  fence_after_sync();
 #pragma unroll
   for (int o = 0; o < OUT; ++o) accbo[o] = warp_sum(accbo[o]);
   fence_before_sync();
   __syncthreads();
-  float* sacc = smem + S::WARP;
+  fence_after_sync();
+  float* sacc = smem;
   for (int i = tid; i < S::R_END; i += kThreads) sacc[i] = 0.0f;
   __syncthreads();
   for (int w = 0; w < kWarps; ++w) {
     if (warp == w) {
-      const int jb = lane >> 3, kb = lane & 7;
+      if (L > 1 && wq < 2) {   // dW_2 rows live in TMEM lanes 0-31 (hi*hi | hi*lo) and 32-63 (lo*hi) of every warpgroup
+        uint32_t v[32];
+        tmem_ld32(lane_base + kTmemDW, v);
+        float* dstw = sacc + S::R_H + kHid + lane * kHid;
 #pragma unroll
-      for (int l = 2; l <= L; ++l) {
+        for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
+        if (wq == 0) {
+          tmem_ld32(lane_base + kTmemDW + 32, v);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-#pragma unroll
-          for (int f = 0; f < 4; ++f) sacc[S::R_H + (l - 2) * S::R_HSTRIDE + kHid + (jb + 4 * e) * kHid + kb + 8 * f] += accW[l - 2][e][f];
-        sacc[S::R_H + (l - 2) * S::R_HSTRIDE + lane] += accb[l - 1];
+          for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
+        }
       }
+#pragma unroll
+      for (int l = 2; l <= L; ++l) sacc[S::R_H + (l - 2) * S::R_HSTRIDE + lane] += accb[l - 1];
       sacc[S::R_B1 + lane] += accb[0];
 #pragma unroll
       for (int dd = 0; dd < DIN; ++dd) sacc[S::R_W1 + lane * DIN + dd] += accW1[dd];
@@ -354,8 +414,9 @@ __global__ void __launch_bounds__(kThreads, 3) mlp_tc_bwd_kernel(MlpArgs a) {
     }
     dst[i] = sacc[src];
   }
+  fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
 }
 
 template <int L, int DIN, int OUT>
@@ -401,8 +462,7 @@ int launch_mlp_tc_bwd(const MlpArgs& a, int nets, int chunks, cudaStream_t st) {
   switch (a.net[0].n_hidden) {
     case 1: return bwd_dispatch_din<1>(a, din, out_pad, chunks, nets, st);
     case 2: return bwd_dispatch_din<2>(a, din, out_pad, chunks, nets, st);
-    case 3: return bwd_dispatch_din<3>(a, din, out_pad, chunks, nets, st);
-    case 4: return bwd_dispatch_din<4>(a, din, out_pad, chunks, nets, st);
+    default: return launch_mlp_fast(a, nets, chunks, true, st);   // deeper nets: the CUDA-core kernel (mlp.cu)
   }
   return PACOH_ERR_UNSUPPORTED;
 }

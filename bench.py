@@ -261,10 +261,12 @@ def run_ours(args):
                 "frac": kernels[dom]["tflops"] / ffma_peak, "traffic": traffic,
                 "peak_source": "FFMA micro-benchmark run in this process (pacoh_ffma_peak_launch); MEASURED_PEAKS.json holds no FP32 "
                                "figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s" % nominal,
-                "bound_note": "FP32-compute bound (arithmetic intensity ~5e4 FLOP/B, DRAM < 1% busy). gp_mll runs on the CUDA "
-                              "cores (FFMA); the MLP kernels run their 32x32 hidden-layer contractions on tcgen05 in 3xTF32 "
-                              "(fp32-accurate) and are reported against the same FP32 denominator, so their fraction can "
-                              "exceed what FFMA alone could reach",
+                "bound_note": "FP32-compute bound (arithmetic intensity ~5e4 FLOP/B, DRAM ~1% busy). All three kernels run their "
+                              "matrix work on tcgen05 in 3xTF32 (fp32-accurate): the MLP hidden-layer and weight-gradient "
+                              "contractions and the rank-4 Gauss-Jordan updates of the GP kernel; tanh / exp2 / the 4x4 pivot-block "
+                              "inverses / row sums run on the CUDA cores. Fractions are ALGORITHMIC fp32 FLOPs over the measured FP32 "
+                              "FFMA peak (the honest denominator for an fp32-parity path), so a kernel can exceed what FFMA alone "
+                              "could reach",
                 "step_achieved_tflops": value * flops_per_eval() / 1e12, "step_frac_of_fp32_peak": value * flops_per_eval() / 1e12 / ffma_peak,
                 "kernels": kernels}
 

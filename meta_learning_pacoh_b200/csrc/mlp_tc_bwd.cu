@@ -1,9 +1,11 @@
 // Tensor-core backward pass of the per-particle MLPs (recompute-forward + reverse pass), sm_100a.
 //
 // Same semantics as mlp_bwd_kernel in mlp.cu (the autograd reverse pass through NeuralNetworkVectorized,
-// meta_learn/models.py:295-317, 343-349, svgd.py:16).  One CTA = THREE independent warpgroups that share the staged
-// weights; each warpgroup walks its own 128-point tiles (thread t owns point t) with its own tensor-memory columns,
-// mbarriers and named barrier, so the three tile pipelines hide each other's MMA / barrier round trips.
+// meta_learn/models.py:295-317, 343-349, svgd.py:16).  One CTA = THREE independent 256-thread warpgroups that share the
+// staged weights; each warpgroup walks its own 128-point tiles with its own tensor-memory columns, mbarriers and named
+// barrier, so the three tile pipelines hide each other's MMA / barrier round trips.  TWO threads share a point (16 of
+// the 32 features each; warps w and w + 4 address the same 32 TMEM lanes): 24 warps per SM instead of 12 at half the
+// registers per thread -- the elementwise chains (tanh, hi/lo splits, column stores) are latency-bound otherwise.
 //
 //   tensor cores (tcgen05, 3xTF32, accumulators in TMEM)             CUDA cores
 //   ------------------------------------------------------------     ------------------------------------------------
@@ -33,7 +35,8 @@ namespace {
 using namespace tc;
 
 constexpr int kWG = 3;                   // warpgroups (independent tile pipelines) per CTA
-constexpr int kWGThreads = 128;
+constexpr int kWGThreads = 256;          // TWO threads per point: thread (point, half) owns 16 of the 32 features
+constexpr int kFH = 16;
 constexpr int kThreads = kWG * kWGThreads;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 128;
@@ -53,6 +56,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int L, int DIN, int OUT>
 struct BwdSmem {
   static constexpr int LH = L > 1 ? L - 1 : 0;
@@ -60,7 +71,7 @@ struct BwdSmem {
   // by 8 row groups: that stays inside the warpgroup's H^T tile / the next warpgroup's tiles / the weights)
   static constexpr int WG_TILES = (1 + LH) * kStackF;              // dA_l^T, then H_l^T for l = 1..L-1
   static constexpr int B = kWG * WG_TILES;                         // per layer l = 2..L: W hi, W lo, W^T hi, W^T lo (1024 floats each)
-  static constexpr int W1 = B + (LH > 0 ? LH : 1) * 4 * kHid * kHid;   // [32][DIN]
+  static constexpr int W1 = B + LH * 4 * kHid * kHid;              // [32][DIN]
   static constexpr int B1 = W1 + kHid * DIN;
   static constexpr int BH = B1 + kHid;                             // biases of layers 2..L
   static constexpr int WOUT = BH + LH * kHid;                      // [OUT][32]
@@ -91,9 +102,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   __shared__ uint32_t tmem_base_s;
   const NetDev& net = a.net[blockIdx.z];
   const int p = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = tid >> 7, wt = tid & 127, wq = warp & 3;      // warpgroup, thread / warp inside it
+  const int wg = tid >> 8, wt = tid & 255;                       // warpgroup, thread inside it
+  const int wq = (wt >> 5) & 3, fh = wt >> 7;                    // TMEM lane quadrant (points 32 wq + lane), feature half
+  const int f0 = kFH * fh;                                       // this thread's features f0 .. f0 + 15
   const float* th = a.theta + (size_t)p * a.D;
-  float* sw = smem + S::WARP + warp * S::WARP_SIZE;             // this warp's region
+  float* sw = smem + S::WARP + warp * S::WARP_SIZE;              // this warp's region
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid < kWG) { mbar_init(smem_u32(&mbar[tid][0]), 1); mbar_init(smem_u32(&mbar[tid][1]), 1); }
@@ -134,22 +147,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   const uint32_t bar = smem_u32(&mbar[wg][0]), bar_dw = smem_u32(&mbar[wg][1]);
   uint32_t parity = 0, parity_dw = 0;
   bool dw_pending = false;     // dW MMAs in flight still read the transposed tiles
-  auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory"); };
-  // ---- zero the dW accumulator (it is only ever accumulated into)
+  auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" :: "r"(wg + 1) : "memory"); };
+  // ---- zero the dW accumulator (it is only ever accumulated into): each feature half zeroes 32 of the 64 columns
   if (L > 1) {
     uint32_t z[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0u;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_st16(lane_base + kTmemDW + 16 * c, z);
+    tmem_st16(lane_base + kTmemDW + 32 * fh, z);
+    tmem_st16(lane_base + kTmemDW + 32 * fh + 16, z);
     tmem_st_wait();
   }
 
-  // ---- persistent accumulators
-  float accb[L];           // db_l[lane]
-  float accWo[OUT];        // dWout[o][lane]
-  float accbo[OUT];        // dbout[o], per-thread partial over its own points
-  float accW1[DIN];        // dW1[lane][dd]
+  // ---- persistent accumulators.  Row sums are taken lane-per-feature over this warp's OWN 16 rows: lane l owns row
+  //      f0 + (l & 15) and the point chunks 4 (l >> 4) .. + 3 of the warp's 32 points; halves are combined at the end.
+  float accb[L];           // db_l[row]
+  float accWo[OUT];        // dWout[o][row]
+  float accbo[OUT];        // dbout[o], per-thread partial over its own points (feature half 0 only)
+  float accW1[DIN];        // dW1[row][dd]
 #pragma unroll
   for (int l = 0; l < L; ++l) accb[l] = 0.0f;
 #pragma unroll
@@ -163,8 +177,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   const int t0 = (int)(((long long)tiles * blockIdx.x) / gridDim.x), t1 = (int)(((long long)tiles * (blockIdx.x + 1)) / gridDim.x);
 
   // this point's inputs / output gradients; the loads for the NEXT tile are issued one tile ahead (latency hidden)
+  const int pt = wq * 32 + lane;
   auto load_point = [&](int tile_i, float (&xo)[DIN], float (&dro)[OUT]) {
-    const int qq = tile_i * kTile + wt;
+    const int qq = tile_i * kTile + pt;
     const bool ok = tile_i < t1 && qq < Q;
     int src = 0;
     if (ok) {
@@ -180,23 +195,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   float xn[DIN], drn[OUT];
   load_point(t0 + wg, xn, drn);
 
-  // ---- addressing of the stacked SWIZZLE_128B tiles.  Row r, this warp's K-block, point = lane:
+  // ---- addressing of the stacked SWIZZLE_128B tiles.  Row r, K-block wq, point = lane:
   //      float offset = wq * 2048 + (r >> 3) * 256 + (r & 7) * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)
   float* AT = smem + wg * S::WG_TILES;               // dA_l^T stack (values rows 0-31, lo rows 32-63)
-  float* kblk = AT + wq * 2048;                      // this warp's K-block of the dA^T stack
+  float* kblk = AT + wq * 2048 + (f0 >> 3) * 256;    // this warp's K-block of the dA^T stack, at its first row group
   int xo[8];                                         // swizzled position of this point inside row (r & 7) == j
 #pragma unroll
   for (int j = 0; j < 8; ++j) xo[j] = (((lane >> 2) ^ j) << 2) + (lane & 3);
-  const int rrow = (lane >> 3) * 256 + (lane & 7) * 32;   // row `lane` (lane-per-feature reads)
-  const int rsw = (lane & 7) << 2;                        // its swizzle: logical chunk c sits at float offset ((4 c) ^ rsw)
-  // this point's column -> rows 0-31 (value) and 32-63 (lo) of a stacked tile's K-block
-  auto publish_col = [&](float* kb, const float (&v)[kHid]) {
+  const int rl = lane & 15;                                   // row-sum lane mapping: row f0 + rl ...
+  const int rrow = (rl >> 3) * 256 + (rl & 7) * 32;           // ... relative to kblk
+  const int rsw = (rl & 7) << 2;                              // its swizzle: logical chunk c sits at float offset ((4 c) ^ rsw)
+  const int c0 = (lane >> 4) * 4;                             // ... and point chunks c0 .. c0 + 3
+  // this point's 16-feature column slice -> rows f0.. (value) and 32 + f0.. (lo) of a stacked tile's K-block
+  auto publish_col = [&](float* kb, const float (&v)[kFH]) {
 #pragma unroll
-    for (int f = 0; f < kHid; ++f) {
-      const int o = (f >> 3) * 256 + (f & 7) * 32 + xo[f & 7];
-      kb[o] = v[f];
-      kb[o + 1024] = v[f] - tf32_hi(v[f]);
+    for (int e = 0; e < kFH; ++e) {
+      const int o = (e >> 3) * 256 + (e & 7) * 32 + xo[e & 7];
+      kb[o] = v[e];
+      kb[o + 1024] = v[e] - tf32_hi(v[e]);
     }
+  };
+  // ... and -> hi / lo halves of the TMEM A operand (columns f0 .. f0 + 15 of this point's lane)
+  auto store_a_half = [&](const float (&v)[kFH]) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float hv = tf32_hi(v[e]);
+      hi[e] = __float_as_uint(hv);
+      lo[e] = __float_as_uint(v[e] - hv);
+    }
+    tmem_st16(lane_base + kTmemAhi + f0, hi);
+    tmem_st16(lane_base + kTmemAlo + f0, lo);
+    tmem_st_wait();
+  };
+  auto park_col = [&](const float (&v)[kFH]) {      // values only (lane-per-feature row sums)
+#pragma unroll
+    for (int e = 0; e < kFH; ++e) kblk[(e >> 3) * 256 + (e & 7) * 32 + xo[e & 7]] = v[e];
   };
   auto wait_dw = [&]() {
     if (dw_pending) {
@@ -217,19 +251,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
     for (int o = 0; o < OUT; ++o) {
       dr[o] = drn[o];
       sw[S::DOUT + o * 32 + lane] = dr[o];
-      accbo[o] += dr[o];
+      if (fh == 0) accbo[o] += dr[o];
     }
     load_point(tile + kWG, xn, drn);
     // ---- forward recompute: layer 1 in registers, layers 2..L on the tensor cores; H_l^T kept in the transposed tiles
-    float h[kHid];
+    float h[kFH];
 #pragma unroll
-    for (int j4 = 0; j4 < kHid; j4 += 4) {
-      const float4 b = lds4(smem + S::B1 + j4);
+    for (int j4 = 0; j4 < kFH; j4 += 4) {
+      const float4 b = lds4(smem + S::B1 + f0 + j4);
       float acc[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
 #pragma unroll
-        for (int dd = 0; dd < DIN; ++dd) acc[e] = fmaf(smem[S::W1 + (j4 + e) * DIN + dd], x[dd], acc[e]);
+        for (int dd = 0; dd < DIN; ++dd) acc[e] = fmaf(smem[S::W1 + (f0 + j4 + e) * DIN + dd], x[dd], acc[e]);
         h[j4 + e] = tanh_fast(acc[e]);
       }
     }
@@ -237,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
 #pragma unroll
     for (int l = 2; l <= L; ++l) {
       publish_col(kblk + (l - 1) * kStackF, h);     // H_{l-1}^T
-      store_a_tmem(lane_base, h);                   // A operand of the recompute GEMM: this point's row -> its TMEM lane
+      store_a_half(h);                              // A operand of the recompute GEMM: this point's row -> its TMEM lane
       fence_before_sync();
       wg_sync();
       if (wt == 0) {
@@ -248,11 +282,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
       mbar_wait(bar, parity);
       parity ^= 1;
       fence_after_sync();
-      uint32_t v[32];
-      tmem_ld32(lane_base + kTmemD, v);
+      uint32_t v[16];
+      tmem_ld16(lane_base + kTmemD + f0, v);
 #pragma unroll
-      for (int j4 = 0; j4 < kHid; j4 += 4) {
-        const float4 b = lds4(smem + S::BH + (l - 2) * kHid + j4);
+      for (int j4 = 0; j4 < kFH; j4 += 4) {
+        const float4 b = lds4(smem + S::BH + (l - 2) * kHid + f0 + j4);
         h[j4] = tanh_fast(__uint_as_float(v[j4]) + b.x);
         h[j4 + 1] = tanh_fast(__uint_as_float(v[j4 + 1]) + b.y);
         h[j4 + 2] = tanh_fast(__uint_as_float(v[j4 + 2]) + b.z);
@@ -260,26 +294,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
       }
     }
     // ---- output layer backward.  dWout[o][j] += sum_pt H_L[pt][j] dout[pt][o] as a lane-per-feature row sum over
-    //      H_L^T, parked in the value rows of this warp's (idle) dA^T K-block
-#pragma unroll
-    for (int f = 0; f < kHid; ++f) kblk[(f >> 3) * 256 + (f & 7) * 32 + xo[f & 7]] = h[f];
+    //      H_L^T, parked in the value rows of this warp's (idle) slice of the dA^T K-block
+    park_col(h);
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 hv = lds4(kblk + rrow + ((4 * c) ^ rsw));
+    for (int c = 0; c < 4; ++c) {
+      const float4 hv = lds4(kblk + rrow + ((4 * (c0 + c)) ^ rsw));
 #pragma unroll
       for (int o = 0; o < OUT; ++o) {
-        const float4 dv = lds4(sw + S::DOUT + o * 32 + 4 * c);
+        const float4 dv = lds4(sw + S::DOUT + o * 32 + 4 * (c0 + c));
         accWo[o] += fmaf(hv.x, dv.x, fmaf(hv.y, dv.y, fmaf(hv.z, dv.z, hv.w * dv.w)));
       }
     }
-    float da[kHid];
+    float da[kFH];
 #pragma unroll
-    for (int j4 = 0; j4 < kHid; j4 += 4) {
+    for (int j4 = 0; j4 < kFH; j4 += 4) {
       float dh[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int o = 0; o < OUT; ++o) {
-        const float4 w = lds4(smem + S::WOUT + o * kHid + j4);
+        const float4 w = lds4(smem + S::WOUT + o * kHid + f0 + j4);
         dh[0] = fmaf(w.x, dr[o], dh[0]); dh[1] = fmaf(w.y, dr[o], dh[1]); dh[2] = fmaf(w.z, dr[o], dh[2]); dh[3] = fmaf(w.w, dr[o], dh[3]);
       }
 #pragma unroll
@@ -289,10 +322,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
     // ---- hidden layers L..2
 #pragma unroll
     for (int l = L; l >= 2; --l) {
-      float* HTk = kblk + (l - 1) * kStackF;        // this warp's K-block of the H_{l-1}^T stack
+      float* HTk = kblk + (l - 1) * kStackF;        // this warp's slice of the H_{l-1}^T stack
       wait_dw();
       publish_col(kblk, da);                        // dA_l^T
-      store_a_tmem(lane_base, da);
+      store_a_half(da);
       fence_async_smem();                           // transposed tiles (generic-proxy stores) -> visible to the MMA
       fence_before_sync();
       wg_sync();
@@ -312,12 +345,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
         umma_commit(bar_dw);
       }
       dw_pending = true;
-      // ---- while the MMAs run: db_l[lane] = row sum of dA_l^T over this warp's points
+      // ---- while the MMAs run: db_l[row] = row sum of dA_l^T over this lane's half of the warp's points
       {
         float s = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v4 = lds4(kblk + rrow + ((4 * c) ^ rsw));   // swizzled order: conflict-free, and a sum does not care
+        for (int c = 0; c < 4; ++c) {
+          const float4 v4 = lds4(kblk + rrow + ((4 * (c0 + c)) ^ rsw));
           s += (v4.x + v4.y) + (v4.z + v4.w);
         }
         accb[l - 1] += s;
@@ -325,28 +358,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
       mbar_wait(bar, parity);
       parity ^= 1;
       fence_after_sync();
-      uint32_t v[32];
-      tmem_ld32(lane_base + kTmemD, v);
+      uint32_t v[16];
+      tmem_ld16(lane_base + kTmemD + f0, v);
 #pragma unroll
-      for (int k = 0; k < kHid; ++k) {
-        const float hp = HTk[(k >> 3) * 256 + (k & 7) * 32 + xo[k & 7]];
-        da[k] = __uint_as_float(v[k]) * fmaf(-hp, hp, 1.0f);
+      for (int e = 0; e < kFH; ++e) {
+        const float hp = HTk[(e >> 3) * 256 + (e & 7) * 32 + xo[e & 7]];
+        da[e] = __uint_as_float(v[e]) * fmaf(-hp, hp, 1.0f);
       }
     }
     // ---- first layer: db1, dW1 as lane-per-feature row sums over dA_1^T (parked in the dA^T K-block again)
     {
       wait_dw();                                    // the dW MMAs are done reading the dA^T stack
-#pragma unroll
-      for (int f = 0; f < kHid; ++f) kblk[(f >> 3) * 256 + (f & 7) * 32 + xo[f & 7]] = da[f];
+      park_col(da);
       __syncwarp();
       float s = 0.0f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v4 = lds4(kblk + rrow + ((4 * c) ^ rsw));
+      for (int c = 0; c < 4; ++c) {
+        const float4 v4 = lds4(kblk + rrow + ((4 * (c0 + c)) ^ rsw));
         s += (v4.x + v4.y) + (v4.z + v4.w);
 #pragma unroll
         for (int dd = 0; dd < DIN; ++dd) {
-          const float4 xv = lds4(sw + S::X + dd * 32 + 4 * c);
+          const float4 xv = lds4(sw + S::X + dd * 32 + 4 * (c0 + c));
           accW1[dd] += fmaf(v4.x, xv.x, fmaf(v4.y, xv.y, fmaf(v4.z, xv.z, v4.w * xv.w)));
         }
       }
@@ -358,8 +390,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   // ---- reduce: warps in a fixed order into the padded layout (aliasing warpgroup 0's tiles), then un-pad to the flat order
   wait_dw();
   fence_after_sync();
+  // combine the two point halves of every row sum; lanes 0-15 then hold row f0 + lane
 #pragma unroll
-  for (int o = 0; o < OUT; ++o) accbo[o] = warp_sum(accbo[o]);
+  for (int l = 0; l < L; ++l) accb[l] += __shfl_xor_sync(0xffffffffu, accb[l], 16);
+#pragma unroll
+  for (int dd = 0; dd < DIN; ++dd) accW1[dd] += __shfl_xor_sync(0xffffffffu, accW1[dd], 16);
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) {
+    accWo[o] += __shfl_xor_sync(0xffffffffu, accWo[o], 16);
+    accbo[o] = warp_sum(accbo[o]);
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -368,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   __syncthreads();
   for (int w = 0; w < kWarps; ++w) {
     if (warp == w) {
-      if (L > 1 && wq < 2) {   // dW_2 rows live in TMEM lanes 0-31 (hi*hi | hi*lo) and 32-63 (lo*hi) of every warpgroup
+      if (L > 1 && fh == 0 && wq < 2) {   // dW_2 rows live in TMEM lanes 0-31 (hi*hi | hi*lo) and 32-63 (lo*hi) of every warpgroup
         uint32_t v[32];
         tmem_ld32(lane_base + kTmemDW, v);
         float* dstw = sacc + S::R_H + kHid + lane * kHid;
@@ -380,15 +420,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
           for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
         }
       }
+      if (lane < 16) {
+        const int row = f0 + lane;
 #pragma unroll
-      for (int l = 2; l <= L; ++l) sacc[S::R_H + (l - 2) * S::R_HSTRIDE + lane] += accb[l - 1];
-      sacc[S::R_B1 + lane] += accb[0];
+        for (int l = 2; l <= L; ++l) sacc[S::R_H + (l - 2) * S::R_HSTRIDE + row] += accb[l - 1];
+        sacc[S::R_B1 + row] += accb[0];
 #pragma unroll
-      for (int dd = 0; dd < DIN; ++dd) sacc[S::R_W1 + lane * DIN + dd] += accW1[dd];
+        for (int dd = 0; dd < DIN; ++dd) sacc[S::R_W1 + row * DIN + dd] += accW1[dd];
 #pragma unroll
-      for (int o = 0; o < OUT; ++o) {
-        sacc[S::R_WO + o * kHid + lane] += accWo[o];
-        if (lane == 0) sacc[S::R_BO + o] += accbo[o];
+        for (int o = 0; o < OUT; ++o) sacc[S::R_WO + o * kHid + row] += accWo[o];
+      }
+      if (lane == 0 && fh == 0) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) sacc[S::R_BO + o] += accbo[o];
       }
     }
     __syncthreads();
@@ -423,6 +467,9 @@ template <int L, int DIN, int OUT>
 int launch_tc_bwd(const MlpArgs& a, int chunks, int nets, cudaStream_t st) {
   using S = BwdSmem<L, DIN, OUT>;
   const size_t smem = sizeof(float) * S::END;
+  // wide input / output layers (d > 2 together with out > 2 ...) do not leave room for three warpgroups of transposed
+  // tiles in the 227 KB of shared memory: those shapes run on the CUDA-core kernel (mlp.cu)
+  if (smem + 256 > 227 * 1024) return launch_mlp_fast(a, nets, chunks, true, st);
   PACOH_CUDA_CHECK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<L, DIN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(chunks, a.P, nets);
   mlp_tc_bwd_kernel<L, DIN, OUT><<<grid, kThreads, smem, st>>>(a);

@@ -1,5 +1,7 @@
-"""Helper run in a subprocess by test_gpu_parity.py with PACOH_MLP_FWD=ffma PACOH_MLP_BWD=ffma: checks the CUDA-core
-versions of the MLP kernels (mlp.cu) against the fp64 oracle on a few shapes.  Exit code 0 = parity holds."""
+"""Helper run in a subprocess by test_gpu_parity.py with the kernel-selection environment variables set (they are read
+once per process): `ffma` -> PACOH_MLP_FWD=ffma PACOH_MLP_BWD=ffma, the CUDA-core MLP kernels of mlp.cu; `gpwarp` ->
+PACOH_GP=warp, the register (warp-per-matrix) GP kernel for 32 < n <= 64.  Checks them against the fp64 oracle on a few
+shapes.  Exit code 0 = parity holds."""
 import os
 import sys
 
@@ -11,11 +13,16 @@ sys.path.insert(0, ROOT)
 from oracle import pacoh_oracle as orc  # noqa: E402
 from meta_learning_pacoh_b200 import engine as eng  # noqa: E402
 
-assert os.environ.get("PACOH_MLP_FWD") == "ffma" and os.environ.get("PACOH_MLP_BWD") == "ffma"
+mode = sys.argv[1] if len(sys.argv) > 1 else "ffma"
+if mode == "ffma":
+    assert os.environ.get("PACOH_MLP_FWD") == "ffma" and os.environ.get("PACOH_MLP_BWD") == "ffma"
+else:
+    assert os.environ.get("PACOH_GP") == "warp"
 dev = "cuda:0"
 worst = 0.0
 for kw, n in ((dict(input_dim=1), 50), (dict(input_dim=2, mean_layers=(16,), kernel_layers=(8, 24, 16)), 13),
-              (dict(input_dim=1, mean_layers=(32,) * 4, kernel_layers=(32,) * 4), 20)):
+              (dict(input_dim=1, mean_layers=(32,) * 4, kernel_layers=(32,) * 4), 20),
+              (dict(input_dim=3, mean_layers=(32, 32), kernel_layers=(32, 32), feature_dim=4), 41)):
     rs = np.random.RandomState(n)
     x = rs.uniform(-2, 2, size=(6, n, kw["input_dim"])).astype(np.float32)
     y = (np.sin(2 * x[..., 0]) + 0.1 * rs.normal(size=(6, n))).astype(np.float32)
@@ -33,5 +40,5 @@ for kw, n in ((dict(input_dim=1), 50), (dict(input_dim=2, mean_layers=(16,), ker
     err_l = (logp.cpu().double() - logp64).abs().max().item() / logp64.abs().max().item()
     err_g = (dth.cpu().double() - g64).abs().max().item() / g64.abs().max().item()
     worst = max(worst, err_l, err_g)
-    print("ffma path", kw, "logp rel %.2e grad rel %.2e" % (err_l, err_g))
+    print(mode, "path", kw, "logp rel %.2e grad rel %.2e" % (err_l, err_g))
 sys.exit(0 if worst <= 1e-4 else 1)

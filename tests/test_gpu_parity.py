@@ -171,6 +171,27 @@ def test_architectures_match_oracle(eng, kw):
     assert_groups(arch, score, g64)
 
 
+@pytest.mark.parametrize("n,kw", [
+    (50, dict(input_dim=3, mean_layers=(32, 32), kernel_layers=(32, 32), feature_dim=4)),    # FT = 4 instantiation
+    (33, dict(input_dim=3, mean_kind="NN", covar_kind="SE")),                                 # F = 3, raw inputs as features
+    (64, dict(input_dim=2, mean_layers=(32, 32), kernel_layers=(16, 16), feature_dim=1)),    # full 64 rows, F = 1
+    (41, dict(input_dim=2, mean_kind="zero", covar_kind="NN")),
+    (57, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),                              # PACOH-MAP variant
+    (50, dict(input_dim=1, mean_kind="constant", covar_kind="SE")),
+])
+def test_tensor_core_gp_kernel_shapes(eng, n, kw):
+    """gp_tc.cu (32 < n <= 64): feature widths, mean kinds, output scale, odd task counts (the dummy second matrix)."""
+    x, y = _synthetic(6, n, d=kw["input_dim"], seed=n)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    theta = _prior_particles(lay, 3, 11 + n)
+    for idx in ([5, 1, 1, 0, 2, 3, 4], [2], [0, 5, 3, 3]):
+        mll, logp, score, info = run_engine(eng, arch, x, y, theta, idx)
+        mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
+        assert (info == 0).all()
+        assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
+        assert_groups(arch, score, g64)
+
+
 def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
     """BASELINE config #1: the engine's P=1 ScaleRBF/noise-floor path reproduces demo.ipynb's 'Loss: 5.755850'."""
     train = orc.sinusoid_tasks(20, 5, seed=26)
@@ -314,5 +335,16 @@ def test_cuda_core_mlp_kernels_still_match_oracle():
     import sys
     env = dict(os.environ, PACOH_MLP_FWD="ffma", PACOH_MLP_BWD="ffma")
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ffma_path_check.py")
-    r = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, script, "ffma"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_register_gp_kernel_still_matches_oracle():
+    """32 < n <= 64 runs on the tensor-memory GP kernel (gp_tc.cu); PACOH_GP=warp selects the register kernel of
+    gp_mll.cu for those sizes (kept for A/B measurements): same subprocess check against the fp64 oracle."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PACOH_GP="warp")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ffma_path_check.py")
+    r = subprocess.run([sys.executable, script, "gpwarp"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
 #pragma unroll
   for (int f = 0; f < RS; ++f) sf[row][f] = f < FT ? u[f] : 0.0f;
   __syncthreads();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);   // provably warp-uniform: MMA operands stay in uniform registers
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t bar = smem_u32(&mbar);
   uint32_t parity = 0;

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kTcThreads) mlp_tc_fwd_kernel(MlpArgs a) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);   // provably warp-uniform: MMA operands stay in uniform registers
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
   const uint32_t bar = smem_u32(&mbar);
   uint32_t parity = 0;

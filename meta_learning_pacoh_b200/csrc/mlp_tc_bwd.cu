@@ -143,6 +143,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s + kTmemWG * wg;                    // this warpgroup's columns
+  // the same values as provably warp-uniform registers: the MMA issue sequences (descriptor arithmetic, UTCHMMA
+  // operands) then stay on the uniform datapath instead of paying one R2UR per operand per instruction
+  // (recomputed right before every issue: two shuffles are cheaper than four more live registers)
+#define PACOH_UNIFORM_CTX()                                                                     \
+  const int wg_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 8), 0);                       \
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base_s, 0) + kTmemWG * wg_u;           \
+  const uint32_t bar_u = smem_u32(&mbar[wg_u][0]), bar_dw_u = smem_u32(&mbar[wg_u][1]);        \
+  const uint32_t at_u = smem_u32(smem + wg_u * S::WG_TILES);                                   \
+  (void)bar_dw_u; (void)at_u;
   const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);       // this warp's 32 TMEM lanes
   const uint32_t bar = smem_u32(&mbar[wg][0]), bar_dw = smem_u32(&mbar[wg][1]);
   uint32_t parity = 0, parity_dw = 0;
@@ -196,12 +205,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   load_point(t0 + wg, xn, drn);
 
   // ---- addressing of the stacked SWIZZLE_128B tiles.  Row r, K-block wq, point = lane:
-  //      float offset = wq * 2048 + (r >> 3) * 256 + (r & 7) * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)
+  //      float offset = wq * 2048 + (r >> 3) * 256 + (r & 7) * 32 + (lane ^ ((r & 7) << 2))
   float* AT = smem + wg * S::WG_TILES;               // dA_l^T stack (values rows 0-31, lo rows 32-63)
   float* kblk = AT + wq * 2048 + (f0 >> 3) * 256;    // this warp's K-block of the dA^T stack, at its first row group
-  int xo[8];                                         // swizzled position of this point inside row (r & 7) == j
-#pragma unroll
-  for (int j = 0; j < 8; ++j) xo[j] = (((lane >> 2) ^ j) << 2) + (lane & 3);
+  // swizzled position of this point inside row r: (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3) == lane ^ ((r & 7) << 2)
+#define PACOH_XO(j) (lane ^ ((j) << 2))
   const int rl = lane & 15;                                   // row-sum lane mapping: row f0 + rl ...
   const int rrow = (rl >> 3) * 256 + (rl & 7) * 32;           // ... relative to kblk
   const int rsw = (rl & 7) << 2;                              // its swizzle: logical chunk c sits at float offset ((4 c) ^ rsw)
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   auto publish_col = [&](float* kb, const float (&v)[kFH]) {
 #pragma unroll
     for (int e = 0; e < kFH; ++e) {
-      const int o = (e >> 3) * 256 + (e & 7) * 32 + xo[e & 7];
+      const int o = (e >> 3) * 256 + (e & 7) * 32 + PACOH_XO(e & 7);
       kb[o] = v[e];
       kb[o + 1024] = v[e] - tf32_hi(v[e]);
     }
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   };
   auto park_col = [&](const float (&v)[kFH]) {      // values only (lane-per-feature row sums)
 #pragma unroll
-    for (int e = 0; e < kFH; ++e) kblk[(e >> 3) * 256 + (e & 7) * 32 + xo[e & 7]] = v[e];
+    for (int e = 0; e < kFH; ++e) kblk[(e >> 3) * 256 + (e & 7) * 32 + PACOH_XO(e & 7)] = v[e];
   };
   auto wait_dw = [&]() {
     if (dw_pending) {
@@ -274,10 +282,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
       store_a_half(h);                              // A operand of the recompute GEMM: this point's row -> its TMEM lane
       fence_before_sync();
       wg_sync();
+      PACOH_UNIFORM_CTX();
       if (wt == 0) {
         fence_after_sync();
         const uint32_t b_hi = smem_u32(smem + S::B + (l - 2) * 4 * kHid * kHid);
-        gemm128x32x32_3xtf32_ts(tmem, b_hi, b_hi + kHid * kHid * 4, bar);
+        gemm128x32x32_3xtf32_ts(tmem_u, b_hi, b_hi + kHid * kHid * 4, bar_u);
       }
       mbar_wait(bar, parity);
       parity ^= 1;
@@ -329,20 +338,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
       fence_async_smem();                           // transposed tiles (generic-proxy stores) -> visible to the MMA
       fence_before_sync();
       wg_sync();
+      PACOH_UNIFORM_CTX();
       if (wt == 0) {
         fence_after_sync();
         const uint32_t bt_hi = smem_u32(smem + S::B + (l - 2) * 4 * kHid * kHid + 2 * kHid * kHid);
-        gemm128x32x32_3xtf32_ts(tmem, bt_hi, bt_hi + kHid * kHid * 4, bar);              // dH_{l-1} = dA_l W_l
+        gemm128x32x32_3xtf32_ts(tmem_u, bt_hi, bt_hi + kHid * kHid * 4, bar_u);          // dH_{l-1} = dA_l W_l
       } else if (wt == 32) {                        // a second issuer: the weight-gradient GEMM, on its own barrier
         fence_after_sync();
         const uint32_t idesc = umma_idesc_tf32(128, 64);
-        const uint64_t da0 = umma_desc_sw128(smem_u32(AT)), db0 = umma_desc_sw128(smem_u32(AT + (l - 1) * kStackF));
+        const uint64_t da0 = umma_desc_sw128(at_u), db0 = umma_desc_sw128(at_u + (l - 1) * kStackF * 4);
 #pragma unroll
         for (int w = 0; w < 4; ++w)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)            // 8 points = 32 B inside the 128-byte swizzle row; K-block = 8 KB
-            umma_tf32(tmem + kTmemDW, da0 + (uint64_t)(w * 512 + ks * 2), db0 + (uint64_t)(w * 512 + ks * 2), idesc, 1);
-        umma_commit(bar_dw);
+            umma_tf32(tmem_u + kTmemDW, da0 + (uint64_t)(w * 512 + ks * 2), db0 + (uint64_t)(w * 512 + ks * 2), idesc, 1);
+        umma_commit(bar_dw_u);
       }
       dw_pending = true;
       // ---- while the MMAs run: db_l[row] = row sum of dA_l^T over this lane's half of the warp's points
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
       tmem_ld16(lane_base + kTmemD + f0, v);
 #pragma unroll
       for (int e = 0; e < kFH; ++e) {
-        const float hp = HTk[(e >> 3) * 256 + (e & 7) * 32 + xo[e & 7]];
+        const float hp = HTk[(e >> 3) * 256 + (e & 7) * 32 + PACOH_XO(e & 7)];
         da[e] = __uint_as_float(v[e]) * fmaf(-hp, hp, 1.0f);
       }
     }

@@ -152,13 +152,15 @@ __device__ __forceinline__ void store_a_tmem(uint32_t lane_base, const float (&h
 // D[128 x 32] = A[128 x 32] * B[32 x 32]^T in 3xTF32 with A in TMEM, B (hi / lo, 32-row K-major tiles) in shared memory.
 __device__ __forceinline__ void gemm128x32x32_3xtf32_ts(uint32_t tmem, uint32_t b_hi, uint32_t b_lo, uint32_t bar) {
   const uint32_t idesc = umma_idesc_tf32(128, 32);
+  const uint64_t dhi = umma_desc(b_hi, 32 * 16, 128), dlo = umma_desc(b_lo, 32 * 16, 128);
   uint32_t acc = 0;
 #pragma unroll
   for (int ps = 0; ps < 3; ++ps) {                    // lo*hi, hi*lo, hi*hi
-    const uint32_t a_col = ps == 0 ? kTmemAlo : kTmemAhi, sb = ps == 1 ? b_lo : b_hi;
+    const uint32_t a_col = ps == 0 ? kTmemAlo : kTmemAhi;
+    const uint64_t db = ps == 1 ? dlo : dhi;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {                  // K = 32 = 4 x 8 (8 TMEM columns per step)
-      umma_tf32_ts(tmem + kTmemD, tmem + a_col + ks * 8, umma_desc(sb + ks * 2 * 32 * 16, 32 * 16, 128), idesc, acc);
+    for (int ks = 0; ks < 4; ++ks) {                  // K = 32 = 4 x 8 (8 TMEM columns / two 32-row K-chunk planes per step)
+      umma_tf32_ts(tmem + kTmemD, tmem + a_col + ks * 8, db + (uint64_t)(ks * ((2 * 32 * 16) >> 4)), idesc, acc);
       acc = 1;
     }
   }

@@ -26,7 +26,7 @@ using namespace tc;
 
 constexpr int kTcThreads = 128;
 constexpr int kTcTile = 128;
-constexpr int kFwdMinSmemBytes = 56 * 1024;   // caps residency at 4 CTAs/SM = 4 x 128 TMEM columns (the whole tensor memory)
+constexpr int kFwdMinSmemBytes = 50 * 1024;   // caps residency at 4 CTAs/SM = 4 x 128 TMEM columns (the whole tensor memory); 4 x (50 + 1) KB fit, 5 do not
 
 template <int L, int DIN, int OUT>
 struct TcSmem {

@@ -121,11 +121,20 @@ int pacoh_logprob_finalize(int32_t P, int64_t D, const float* theta, const float
  *   bandwidth h > 0 fixed, or h <= 0: median heuristic  h^2 = median(d2 over all P*P) / (2 log(P+1))
  *   phi = (K score + 2 gamma (rowsum(K) * theta - K theta)) / P
  * gamma_out (1 float, device) receives gamma.  workspace: pacoh_svgd_workspace_bytes(P, D).
+ *
+ * The kernel matrix depends on the particles only, not on the scores, so the call is also exposed in two stages:
+ * pacoh_svgd_kernel_matrix (distances, median, K, row sums -> workspace, gamma) may run on a side stream WHILE the
+ * batched MLL forward/backward computes the scores; pacoh_svgd_phi_apply then only contracts K with score / theta.
+ * pacoh_svgd_phi = both stages back to back on one stream.
  */
 int64_t pacoh_svgd_workspace_bytes(int32_t P, int64_t D);
 int pacoh_svgd_phi(int32_t P, int64_t D, const float* theta, const float* score, float bandwidth,
                    int32_t kernel_kind, float* phi, float* gamma_out, void* workspace,
                    int64_t workspace_bytes, void* stream);
+int pacoh_svgd_kernel_matrix(int32_t P, int64_t D, const float* theta, float bandwidth, int32_t kernel_kind,
+                             float* gamma_out, void* workspace, int64_t workspace_bytes, void* stream);
+int pacoh_svgd_phi_apply(int32_t P, int64_t D, const float* theta, const float* score, int32_t kernel_kind,
+                         float* phi, const float* gamma, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Diagonal-Gaussian VI posterior (RandomGPPosterior cov_type='diag', random_gp.py:244-263;

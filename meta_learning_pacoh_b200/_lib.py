@@ -19,7 +19,7 @@ SVGD_RBF, SVGD_IMQ = 0, 1
 EXPORTED_SYMBOLS = [
     "pacoh_abi_version", "pacoh_last_error", "pacoh_param_count", "pacoh_hyper_prior_params",
     "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_logprob_finalize", "pacoh_svgd_workspace_bytes",
-    "pacoh_svgd_phi", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
+    "pacoh_svgd_phi", "pacoh_svgd_kernel_matrix", "pacoh_svgd_phi_apply", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
     "pacoh_stage_timing_enable", "pacoh_stage_timing_read", "pacoh_gp_forward", "pacoh_gp_forward_workspace_bytes",
 ]
 
@@ -67,6 +67,10 @@ def _load():
     lib.pacoh_svgd_workspace_bytes.argtypes = [i32, i64]
     lib.pacoh_svgd_phi.restype = ctypes.c_int
     lib.pacoh_svgd_phi.argtypes = [i32, i64, vp, vp, f32, i32, vp, vp, vp, i64, vp]
+    lib.pacoh_svgd_kernel_matrix.restype = ctypes.c_int
+    lib.pacoh_svgd_kernel_matrix.argtypes = [i32, i64, vp, f32, i32, vp, vp, i64, vp]
+    lib.pacoh_svgd_phi_apply.restype = ctypes.c_int
+    lib.pacoh_svgd_phi_apply.argtypes = [i32, i64, vp, vp, i32, vp, vp, vp, i64, vp]
     lib.pacoh_vi_sample.restype = ctypes.c_int
     lib.pacoh_vi_sample.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp]
     lib.pacoh_vi_grad.restype = ctypes.c_int

@@ -147,25 +147,33 @@ extern "C" int64_t pacoh_svgd_workspace_bytes(int32_t P, int64_t D) {
   return (int64_t)sizeof(float) * (chunks * P * P + (int64_t)P * P + P + 64);
 }
 
-extern "C" int pacoh_svgd_phi(int32_t P, int64_t D, const float* theta, const float* score, float bandwidth,
-                              int32_t kernel_kind, float* phi, float* gamma_out, void* workspace, int64_t workspace_bytes,
-                              void* stream) {
-  if (P < 1 || D < 1 || !theta || !score || !phi || !gamma_out || !workspace) {
-    set_error("pacoh_svgd_phi: invalid argument");
+// Argument checks shared by the three SVGD entry points.
+static int svgd_check(const char* fn, int32_t P, int64_t D, int32_t kernel_kind, const void* workspace, int64_t workspace_bytes) {
+  if (P < 1 || D < 1 || !workspace) {
+    set_error("%s: invalid argument", fn);
     return PACOH_ERR_INVALID;
   }
   if (kernel_kind != PACOH_SVGD_RBF) {
-    set_error("pacoh_svgd_phi: only the RBF Stein kernel is implemented (IMQ: SURVEY 8(f).3)");
+    set_error("%s: only the RBF Stein kernel is implemented (IMQ: SURVEY 8(f).3)", fn);
     return PACOH_ERR_UNSUPPORTED;
   }
   if (P > 128) {
-    set_error("pacoh_svgd_phi: P=%d > 128 particles not supported by the single-CTA median", P);
+    set_error("%s: P=%d > 128 particles not supported by the single-CTA median", fn, P);
     return PACOH_ERR_UNSUPPORTED;
   }
   if (workspace_bytes < pacoh_svgd_workspace_bytes(P, D)) {
-    set_error("pacoh_svgd_phi: workspace too small");
+    set_error("%s: workspace too small", fn);
     return PACOH_ERR_WORKSPACE;
   }
+  return PACOH_OK;
+}
+
+// Stage 1 (depends on the particles only): pairwise squared distances, median-heuristic bandwidth, K and its row sums.
+extern "C" int pacoh_svgd_kernel_matrix(int32_t P, int64_t D, const float* theta, float bandwidth, int32_t kernel_kind,
+                                        float* gamma_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = svgd_check("pacoh_svgd_kernel_matrix", P, D, kernel_kind, workspace, workspace_bytes);
+  if (rc != PACOH_OK) return rc;
+  if (!theta || !gamma_out) { set_error("pacoh_svgd_kernel_matrix: invalid argument"); return PACOH_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = (int)((D + kColTile - 1) / kColTile);
   float* partial = (float*)workspace;
@@ -179,9 +187,33 @@ extern "C" int pacoh_svgd_phi(int32_t P, int64_t D, const float* theta, const fl
   PACOH_CUDA_CHECK(cudaFuncSetAttribute(svgd_kernel_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   svgd_kernel_matrix_kernel<<<1, 1024, smem2, st>>>(P, chunks, partial, bandwidth, Kmat, rowsum, gamma_out, np2);
   PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+// Stage 2: phi = (K score + 2 gamma (rowsum(K) * theta - K theta)) / P from the K / row sums / gamma stage 1 left in
+// `workspace` / `gamma` (same particles!).
+extern "C" int pacoh_svgd_phi_apply(int32_t P, int64_t D, const float* theta, const float* score, int32_t kernel_kind,
+                                    float* phi, const float* gamma, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = svgd_check("pacoh_svgd_phi_apply", P, D, kernel_kind, workspace, workspace_bytes);
+  if (rc != PACOH_OK) return rc;
+  if (!theta || !score || !phi || !gamma) { set_error("pacoh_svgd_phi_apply: invalid argument"); return PACOH_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = (int)((D + kColTile - 1) / kColTile);
+  const float* Kmat = (const float*)workspace + (size_t)chunks * P * P;
+  const float* rowsum = Kmat + (size_t)P * P;
   const size_t smem3 = sizeof(float) * ((size_t)P * P + (size_t)P * kColTile);
   PACOH_CUDA_CHECK(cudaFuncSetAttribute(svgd_phi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-  svgd_phi_kernel<<<chunks, 256, smem3, st>>>(P, D, theta, score, Kmat, rowsum, gamma_out, phi);
+  svgd_phi_kernel<<<chunks, 256, smem3, st>>>(P, D, theta, score, Kmat, rowsum, gamma, phi);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
+}
+
+// Both stages back to back on one stream.
+extern "C" int pacoh_svgd_phi(int32_t P, int64_t D, const float* theta, const float* score, float bandwidth,
+                              int32_t kernel_kind, float* phi, float* gamma_out, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+  if (!score || !phi) { set_error("pacoh_svgd_phi: invalid argument"); return PACOH_ERR_INVALID; }
+  int rc = pacoh_svgd_kernel_matrix(P, D, theta, bandwidth, kernel_kind, gamma_out, workspace, workspace_bytes, stream);
+  if (rc != PACOH_OK) return rc;
+  return pacoh_svgd_phi_apply(P, D, theta, score, kernel_kind, phi, gamma_out, workspace, workspace_bytes, stream);
 }

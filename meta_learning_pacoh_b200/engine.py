@@ -251,7 +251,11 @@ def meta_log_prob(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, 
 
 
 class SVGDDirection:
-    """phi = (K s + grad K) / P on device, median heuristic included (pacoh_svgd_phi; svgd.py:12-23, 32-59)."""
+    """phi = (K s + grad K) / P on device, median heuristic included (pacoh_svgd_phi; svgd.py:12-23, 32-59).
+
+    ``prepare(theta)`` starts the score-independent half (pairwise distances, median bandwidth, K, row sums) on a side
+    stream so that it overlaps the batched MLL forward/backward; the following ``__call__(theta, score)`` with the SAME
+    particles then only waits for it and applies K.  Without ``prepare`` the call runs both halves in order."""
 
     def __init__(self, P, D, device, bandwidth=None, kernel="RBF"):
         if kernel != "RBF":
@@ -261,12 +265,36 @@ class SVGDDirection:
         nbytes = check(lib.pacoh_svgd_workspace_bytes(P, D))
         self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         self.gamma = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._side = None            # side stream + event of a pending prepare()
+        self._ready = None
+        self._prepared_for = None
+
+    def prepare(self, theta):
+        theta = _f32c(theta, self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ready = torch.cuda.Event()
+        cur = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur)          # particles of the previous update are final; the last phi_apply is done with K
+        with torch.cuda.stream(self._side):
+            check(lib.pacoh_svgd_kernel_matrix(self.P, self.D, _ptr(theta), self.bandwidth, _lib.SVGD_RBF, _ptr(self.gamma),
+                                               _ptr(self.ws), self.ws.numel(), _stream()))
+            self._ready.record(self._side)
+        self._prepared_for = (theta.data_ptr(), theta._version)
 
     def __call__(self, theta, score, out=None):
         theta, score = _f32c(theta, self.device), _f32c(score, self.device)
         phi = out if out is not None else torch.empty_like(theta)
-        check(lib.pacoh_svgd_phi(self.P, self.D, _ptr(theta), _ptr(score), self.bandwidth, _lib.SVGD_RBF, _ptr(phi),
-                                 _ptr(self.gamma), _ptr(self.ws), self.ws.numel(), _stream()))
+        if self._prepared_for is not None and self._prepared_for == (theta.data_ptr(), theta._version):
+            torch.cuda.current_stream(self.device).wait_event(self._ready)
+            check(lib.pacoh_svgd_phi_apply(self.P, self.D, _ptr(theta), _ptr(score), _lib.SVGD_RBF, _ptr(phi), _ptr(self.gamma),
+                                           _ptr(self.ws), self.ws.numel(), _stream()))
+        else:
+            if self._prepared_for is not None:      # a stale prepare(): let it finish before the workspace is reused
+                torch.cuda.current_stream(self.device).wait_event(self._ready)
+            check(lib.pacoh_svgd_phi(self.P, self.D, _ptr(theta), _ptr(score), self.bandwidth, _lib.SVGD_RBF, _ptr(phi),
+                                     _ptr(self.gamma), _ptr(self.ws), self.ws.numel(), _stream()))
+        self._prepared_for = None
         return phi
 
 

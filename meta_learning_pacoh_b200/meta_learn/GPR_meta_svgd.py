@@ -100,6 +100,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         self._idx_host[:hi - lo].copy_(torch.from_numpy(idx[lo:hi]))
         idx_dev = self._idx_host[:hi - lo].to(self.device, non_blocking=True)
         pre = eng.pre_factor([self.engine.n] * T)                      # GLOBAL batch (random_gp.py:209-212)
+        self._phi.prepare(self.particles)                              # K(theta) on a side stream, under the MLL kernels
         logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
                                                         self._prior_sigma, self.prior_factor, pre, self._group)
         phi = self._phi(self.particles, score)
@@ -128,6 +129,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         se.x.copy_(x_batch[lo:hi], non_blocking=True)
         se.y.copy_(y_batch[lo:hi], non_blocking=True)
         pre = eng.pre_factor([se.n] * T)
+        self._phi.prepare(self.particles)
         logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx, self._prior_mu,
                                                         self._prior_sigma, self.prior_factor, pre, self._group)
         phi = self._phi(self.particles, score)

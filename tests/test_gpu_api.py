@@ -68,6 +68,22 @@ def test_svgd_meta_fit_predict_eval_like_reference_callers(ml):
     assert abs(ll - ll64) <= 1e-4 * max(1.0, abs(ll64)) and abs(rmse - rmse64) <= 1e-4 * rmse64 and abs(cal - cal64) <= 0.021
 
 
+def test_svgd_two_stage_direction_equals_single_call():
+    """pacoh_svgd_kernel_matrix on a side stream + pacoh_svgd_phi_apply == pacoh_svgd_phi (the step overlaps the
+    particle-only half with the MLL kernels); a prepare() for other particles must be ignored, not reused."""
+    from meta_learning_pacoh_b200 import engine as eng
+    g = torch.Generator().manual_seed(5)
+    theta = torch.randn(16, 300, generator=g).cuda()
+    score = torch.randn(16, 300, generator=g).cuda()
+    ref = eng.SVGDDirection(16, 300, "cuda:0")(theta, score)
+    sv = eng.SVGDDirection(16, 300, "cuda:0")
+    sv.prepare(theta)
+    assert torch.equal(sv(theta, score), ref)
+    sv.prepare(theta * 2.0)                       # stale: different tensor
+    assert torch.equal(sv(theta, score), ref)
+    assert torch.equal(sv(theta, score), ref)     # and without any prepare
+
+
 def test_svgd_seed_determinism(ml):
     """tests/test_GPR.py:173-187 style: two runs with the same seed are bit-identical."""
     train, test = orc.sinusoid_tasks(12, 8, seed=3, n_test=20)

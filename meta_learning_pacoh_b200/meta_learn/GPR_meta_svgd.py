@@ -113,24 +113,52 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         self._last_info, self._last_logp = info, logp
         return logp
 
-    def svgd_step_host(self, x_batch, y_batch):
+    def svgd_step_host(self, x_batch, y_batch, global_tasks=None, wait=True):
         """Same update as svgd_step, fed like the reference's closure is (GPR_meta_svgd.py:190-199 receives the sampled
         task tensors themselves): ``x_batch`` (T, n, d) / ``y_batch`` (T, n) are HOST tensors (pinned for async copies)
         holding the sampled, normalised batch in order.  They are copied to the device, the step runs on them with
-        identity task indices, and logp (P,) is returned on the host.  Used for the end-to-end measurement."""
-        T = x_batch.shape[0]
-        lo, hi = eng.shard_bounds(T, self._rank, self._world)
-        if getattr(self, "_stage_engine", None) is None or self._stage_engine.T_total != hi - lo:
-            xs = torch.empty((hi - lo,) + tuple(x_batch.shape[1:]), dtype=torch.float32)
-            ys = torch.empty((hi - lo,) + tuple(y_batch.shape[1:]), dtype=torch.float32)
+        identity task indices, and logp (P,) is read back to the host.  Used for the end-to-end measurement.
+
+        ``global_tasks``: when given, ``x_batch`` / ``y_batch`` are already THIS rank's shard of a ``global_tasks``-task
+        batch (the caller gathered only rows ``shard_bounds(global_tasks, rank, world)``); otherwise the full batch is
+        passed and sliced here.  ``wait=False`` returns ``(logp_pinned, event)`` without synchronising: the device->host
+        copy of logp is in flight and ``event.synchronize()`` must precede any read -- lets the caller prepare the next
+        batch on the host while this step runs (the copies and the read-back still happen every step)."""
+        if global_tasks is None:
+            T = x_batch.shape[0]
+            lo, hi = eng.shard_bounds(T, self._rank, self._world)
+            x_batch, y_batch = x_batch[lo:hi], y_batch[lo:hi]
+        else:
+            T = int(global_tasks)
+            lo, hi = eng.shard_bounds(T, self._rank, self._world)
+            assert x_batch.shape[0] == hi - lo, "pre-sharded batch does not match shard_bounds"
+        Ts = hi - lo
+        if getattr(self, "_stage_engine", None) is None or self._stage_engine.T_total != 2 * Ts:
+            # two device staging halves: the batch of step k+1 is copied (on a copy stream) while step k computes
+            xs = torch.empty((2 * Ts,) + tuple(x_batch.shape[1:]), dtype=torch.float32)
+            ys = torch.empty((2 * Ts,) + tuple(y_batch.shape[1:]), dtype=torch.float32)
             self._stage_engine = eng.MetaMLLEngine(self.arch, xs, ys, self.device)
-            self._stage_idx = torch.arange(hi - lo, dtype=torch.int32, device=self.device)
+            self._stage_idx = [torch.arange(h * Ts, (h + 1) * Ts, dtype=torch.int32, device=self.device) for h in range(2)]
+            self._logp_host = [torch.empty(self.num_particles, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._logp_event = [torch.cuda.Event() for _ in range(2)]
+            self._copy_event = [torch.cuda.Event() for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._logp_slot = 0
+            self._stage_used = [False, False]
         se = self._stage_engine
-        se.x.copy_(x_batch[lo:hi], non_blocking=True)
-        se.y.copy_(y_batch[lo:hi], non_blocking=True)
+        slot = self._logp_slot
+        self._logp_slot ^= 1
+        if self._stage_used[slot]:
+            self._logp_event[slot].synchronize()        # the step that last used this half (two calls ago) is done
+        self._stage_used[slot] = True
+        with torch.cuda.stream(self._copy_stream):
+            se.x[slot * Ts:(slot + 1) * Ts].copy_(x_batch, non_blocking=True)
+            se.y[slot * Ts:(slot + 1) * Ts].copy_(y_batch, non_blocking=True)
+            self._copy_event[slot].record(self._copy_stream)
+        torch.cuda.current_stream(self.device).wait_event(self._copy_event[slot])
         pre = eng.pre_factor([se.n] * T)
         self._phi.prepare(self.particles)
-        logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx, self._prior_mu,
+        logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx[slot], self._prior_mu,
                                                         self._prior_sigma, self.prior_factor, pre, self._group)
         phi = self._phi(self.particles, score)
         if isinstance(self.optimizer, eng.PacohAdam):
@@ -140,7 +168,13 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             self.particles.grad = -phi
             self.optimizer.step()
         self._last_info = info
-        return logp.cpu()
+        out, ev = self._logp_host[slot], self._logp_event[slot]
+        out.copy_(logp, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        if not wait:
+            return out, ev
+        ev.synchronize()
+        return out.clone()
 
     # ------------------------------------------------------------------ prediction
     def predict(self, context_x, context_y, test_x, return_density=False):

@@ -84,20 +84,17 @@ static int sm_count() {
   return sms;
 }
 
-// Number of tile chunks (CTAs per particle per net) of the MLP kernels: the count with the least wave-quantisation
-// loss, fixed per-CTA cost (weight staging, TMEM allocation, final reduction ~ one tile round) included.
-//   backward: ONE 3-warpgroup CTA per SM, each warpgroup walks every third tile of its chunk (the chunk count also
-//             sizes the per-chunk gradient partials);  forward: 4 CTAs per SM, one tile at a time.
-static int mlp_chunks(int P, int nets, int Q, bool bwd) {
+// Number of tile chunks (CTAs per particle per net) of the chunked MLP kernels: the count with the least
+// wave-quantisation loss for `resident` CTAs per SM, fixed per-CTA cost (weight staging, TMEM allocation ~ two tiles)
+// included.  Used by the tensor-core forward (4 CTAs per SM) and the CUDA-core kernels (2 per SM).
+static int mlp_chunks(int P, int nets, int Q, int resident) {
   const int tiles = (Q + kTileP - 1) / kTileP;
-  const long long slots = (long long)sm_count() * (bwd ? 1 : 4), ctas = (long long)P * nets;
+  const long long slots = (long long)sm_count() * resident, ctas = (long long)P * nets;
   const int cmax = std::max(1, std::min(tiles / 8, 256));
   int best = 1;
   long long best_cost = -1;
   for (int c = 1; c <= cmax; ++c) {
-    const long long per = (tiles + c - 1) / c;
-    const long long rounds = bwd ? (per + 2) / 3 + 1 : per + 2;
-    const long long cost = ((ctas * c + slots - 1) / slots) * rounds;
+    const long long cost = ((ctas * c + slots - 1) / slots) * ((tiles + c - 1) / c + 2);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -130,7 +127,7 @@ static int launch_mlp_best(const MlpArgs& ma, int nets, int chunks, bool bwd, cu
 
 struct Plan {
   ModelDev m;
-  int Q, chunks, chunks_fwd;   // chunks: backward kernels (sizes the gradient partials); chunks_fwd: forward kernels
+  int Q, chunks, chunks_fwd;   // chunks: partial-gradient slots / grid.x of the chunked backward kernels; chunks_fwd: forward kernels
   bool mean_nn, kern_nn, mean_fast, kern_fast, fused;   // fused: one launch covers both nets
   size_t off_mean, off_feat, off_dmean, off_dfeat, off_mll, off_hyp, off_pmean, off_pkern, off_gen, total;
 };
@@ -149,8 +146,11 @@ static int make_plan(const pacoh_arch_t* arch, int P, int T, int n, Plan* pl) {
   pl->mean_fast = pl->mean_nn && net_is_fast(m.mean, m.d);
   pl->kern_fast = pl->kern_nn && net_is_fast(m.kern, m.d);
   pl->fused = pl->mean_fast && pl->kern_fast && m.mean.n_hidden == m.kern.n_hidden;
-  pl->chunks = mlp_chunks(P, pl->fused ? 2 : 1, pl->Q, true);
-  pl->chunks_fwd = mlp_chunks(P, pl->fused ? 2 : 1, pl->Q, false);
+  // backward: the tensor-core kernel is persistent (equal tile ranges per SM) and only needs `slots` partial-gradient
+  // slots per (net, particle); the chunked CUDA-core / generic kernels use the chunk count as grid.x.  Both write the
+  // same (chunks, P, D_net) partial layout, so the buffers are sized for the larger of the two.
+  pl->chunks = std::max(mlp_chunks(P, pl->fused ? 2 : 1, pl->Q, 2), mlp_tc_bwd_slots(P, pl->fused ? 2 : 1, pl->Q, nullptr, nullptr));
+  pl->chunks_fwd = mlp_chunks(P, pl->fused ? 2 : 1, pl->Q, 4);
   const size_t PQ = (size_t)P * pl->Q;
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats); return o; };
@@ -371,7 +371,7 @@ extern "C" int pacoh_gp_forward(const pacoh_arch_t* arch, int32_t P, int32_t npt
   memset(&ma, 0, sizeof(ma));
   ma.theta = theta; ma.x = x; ma.task_idx = nullptr;
   ma.P = P; ma.T = 1; ma.n = npts; ma.d = m.d; ma.D = m.D;
-  const int chunks = mlp_chunks(P, 1, npts, false);
+  const int chunks = mlp_chunks(P, 1, npts, 4);
   for (int z = 0; z < 2; ++z) {
     const bool is_nn = z == 0 ? pl.mean_nn : pl.kern_nn;
     float* dst = z == 0 ? mean : feat;

@@ -18,6 +18,7 @@ struct MlpArgs {
 int launch_mlp_fast(const MlpArgs& a, int nets, int chunks, bool bwd, cudaStream_t st);
 int launch_mlp_tc_fwd(const MlpArgs& a, int nets, int chunks, cudaStream_t st);   // tcgen05 forward (mlp_tc.cu)
 int launch_mlp_tc_bwd(const MlpArgs& a, int nets, int chunks, cudaStream_t st);   // tcgen05 + CUDA-core backward (mlp_tc_bwd.cu)
+int mlp_tc_bwd_slots(int P, int nets, int Q, int* grid_out, int* per_cta_out);    // partial slots of its persistent schedule
 int launch_mlp_generic(const MlpArgs& a, int net_index, int chunks, bool bwd, float* scratch, cudaStream_t st);
 size_t mlp_generic_scratch_floats(const NetDev& net, int P, int Q);
 

@@ -24,6 +24,7 @@
 // 16 MMAs per tile instead of 48.  (Layout and truncation validated by tools/ubench/tc_sw128_test.cu.)
 // The dW MMAs are issued by a second thread and committed to their own mbarrier, so they overlap the dH round trip;
 // the operand tiles are only waited for right before they are overwritten.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -44,6 +45,7 @@ constexpr int kStackF = 8192;            // floats of one stacked transposed til
 // tensor-memory columns of one warpgroup: D 32 | A hi 32 | A lo 32 (tc_common.cuh) | dW accumulator 64
 constexpr uint32_t kTmemDW = 96;
 constexpr uint32_t kTmemWG = 160;
+constexpr int kBwdMaxTilesPerAcc = 120;  // persistent schedule: tiles one warpgroup may sum into its TMEM accumulator (see mlp_tc_bwd_slots)
 
 // K-major SWIZZLE_128B shared-memory descriptor: 8-row groups 1024 B apart, start address may advance by 32 B per K-step
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -90,26 +92,47 @@ struct BwdSmem {
   static constexpr int R_BO = R_H + LH * R_HSTRIDE;
   static constexpr int R_WO = R_BO + OUT;
   static constexpr int R_END = R_WO + OUT * kHid;
-  static_assert(R_END <= kStackF, "reduction buffer must fit in one stacked tile");
+  static constexpr int R_PAD = ((R_END + 31) / 32) * 32 + 1;       // per-warp copy stride (odd: the row-major dW stores spread over the banks)
+  static_assert((kWarps + 1) * R_PAD <= kWG * WG_TILES, "reduction buffers must fit in the transposed tiles");
   static_assert(L <= 2, "deeper nets do not fit three warpgroups of transposed tiles in shared memory");
 };
 
 template <int L, int DIN, int OUT>
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a, int nets, int per_cta) {
   using S = BwdSmem<L, DIN, OUT>;
   extern __shared__ __align__(1024) float smem[];
   __shared__ __align__(8) uint64_t mbar[kWG][2];
   __shared__ uint32_t tmem_base_s;
-  const NetDev& net = a.net[blockIdx.z];
-  const int p = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = tid >> 8, wt = tid & 255;                       // warpgroup, thread inside it
   const int wq = (wt >> 5) & 3, fh = wt >> 7;                    // TMEM lane quadrant (points 32 wq + lane), feature half
   const int f0 = kFH * fh;                                       // this thread's features f0 .. f0 + 15
-  const float* th = a.theta + (size_t)p * a.D;
   float* sw = smem + S::WARP + warp * S::WARP_SIZE;              // this warp's region
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid < kWG) { mbar_init(smem_u32(&mbar[tid][0]), 1); mbar_init(smem_u32(&mbar[tid][1]), 1); }
+  uint32_t parity = 0, parity_dw = 0;
+  bool dw_pending = false;     // dW MMAs in flight still read the transposed tiles
+
+  // ---- PERSISTENT CTA: the (net, particle, tile) space is linearised and cut into gridDim.x equal ranges of `per_cta`
+  //      tiles, so every SM gets the same work whatever P, nets and the batch size are (no wave quantisation).  A range
+  //      is processed as segments of one (net, particle) each: stage its weights, walk its tiles, reduce, and write the
+  //      partial gradient into slot (this CTA - first CTA touching that (net, particle)) of the zero-initialised
+  //      (slots, P, D_net) partial buffer.
+  const int Q = a.T * a.n;
+  const int tiles = (Q + kTile - 1) / kTile;
+  const long long total_tiles = (long long)nets * a.P * tiles;
+  const long long g_begin = (long long)blockIdx.x * per_cta;
+  const long long g_end = g_begin + per_cta < total_tiles ? g_begin + per_cta : total_tiles;
+  for (long long g_seg = g_begin; g_seg < g_end;) {
+  const int pn = (int)(g_seg / tiles);                           // (net, particle) of this segment
+  const int zn = pn / a.P, p = pn - zn * a.P;
+  const int t0 = (int)(g_seg - (long long)pn * tiles);
+  const int t1 = (int)((g_end < (long long)(pn + 1) * tiles ? g_end : (long long)(pn + 1) * tiles) - (long long)pn * tiles);
+  const int slot = (int)(blockIdx.x - ((long long)pn * tiles) / per_cta);
+  g_seg += t1 - t0;
+  const NetDev& net = a.net[zn];
+  const float* th = a.theta + (size_t)p * a.D;
   // ---- stage the particle's weights (shared by the three warpgroups)
   const int w0 = net.width[0];
   for (int i = tid; i < kHid * DIN; i += kThreads) {
@@ -154,8 +177,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   (void)bar_dw_u; (void)at_u;
   const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);       // this warp's 32 TMEM lanes
   const uint32_t bar = smem_u32(&mbar[wg][0]), bar_dw = smem_u32(&mbar[wg][1]);
-  uint32_t parity = 0, parity_dw = 0;
-  bool dw_pending = false;     // dW MMAs in flight still read the transposed tiles
   auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" :: "r"(wg + 1) : "memory"); };
   // ---- zero the dW accumulator (it is only ever accumulated into): each feature half zeroes 32 of the 64 columns
   if (L > 1) {
@@ -180,11 +201,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
 #pragma unroll
   for (int dd = 0; dd < DIN; ++dd) accW1[dd] = 0.0f;
 
-  const int Q = a.T * a.n;
-  const int tiles = (Q + kTile - 1) / kTile;
-  // balanced split: chunk sizes differ by at most one tile; inside the CTA the warpgroups interleave
-  const int t0 = (int)(((long long)tiles * blockIdx.x) / gridDim.x), t1 = (int)(((long long)tiles * (blockIdx.x + 1)) / gridDim.x);
-
   // this point's inputs / output gradients; the loads for the NEXT tile are issued one tile ahead (latency hidden)
   const int pt = wq * 32 + lane;
   auto load_point = [&](int tile_i, float (&xo)[DIN], float (&dro)[OUT]) {
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
     }
 #pragma unroll
     for (int dd = 0; dd < DIN; ++dd) xo[dd] = (ok && dd < a.d) ? __ldg(a.x + (size_t)src * a.d + dd) : 0.0f;
-    const float* dsrc = a.dout[blockIdx.z] + ((size_t)p * Q + qq) * net.out_dim;
+    const float* dsrc = a.dout[zn] + ((size_t)p * Q + qq) * net.out_dim;
 #pragma unroll
     for (int o = 0; o < OUT; ++o) dro[o] = (ok && o < net.out_dim) ? __ldg(dsrc + o) : 0.0f;
   };
@@ -413,41 +429,50 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  float* sacc = smem;
-  for (int i = tid; i < S::R_END; i += kThreads) sacc[i] = 0.0f;
+  // every warp drops its contributions into ITS OWN padded copy (kWarps x R_PAD floats over the now idle tiles), then
+  // each entry is summed over the warps in a fixed order: 3 CTA barriers instead of one per warp, bitwise repeatable
+  float* sall = smem;
+  for (int i = tid; i < kWarps * S::R_PAD; i += kThreads) sall[i] = 0.0f;
   __syncthreads();
-  for (int w = 0; w < kWarps; ++w) {
-    if (warp == w) {
-      if (L > 1 && fh == 0 && wq < 2) {   // dW_2 rows live in TMEM lanes 0-31 (hi*hi | hi*lo) and 32-63 (lo*hi) of every warpgroup
-        uint32_t v[32];
-        tmem_ld32(lane_base + kTmemDW, v);
-        float* dstw = sacc + S::R_H + kHid + lane * kHid;
+  {
+    float* mine = sall + warp * S::R_PAD;
+    if (L > 1 && fh == 0 && wq < 2) {   // dW_2 rows live in TMEM lanes 0-31 (hi*hi | hi*lo) and 32-63 (lo*hi) of every warpgroup
+      uint32_t v[32];
+      tmem_ld32(lane_base + kTmemDW, v);
+      float* dstw = mine + S::R_H + kHid + lane * kHid;
+#pragma unroll
+      for (int k = 0; k < kHid; ++k) dstw[k] = __uint_as_float(v[k]);
+      if (wq == 0) {
+        tmem_ld32(lane_base + kTmemDW + 32, v);
 #pragma unroll
         for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
-        if (wq == 0) {
-          tmem_ld32(lane_base + kTmemDW + 32, v);
-#pragma unroll
-          for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
-        }
-      }
-      if (lane < 16) {
-        const int row = f0 + lane;
-#pragma unroll
-        for (int l = 2; l <= L; ++l) sacc[S::R_H + (l - 2) * S::R_HSTRIDE + row] += accb[l - 1];
-        sacc[S::R_B1 + row] += accb[0];
-#pragma unroll
-        for (int dd = 0; dd < DIN; ++dd) sacc[S::R_W1 + row * DIN + dd] += accW1[dd];
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) sacc[S::R_WO + o * kHid + row] += accWo[o];
-      }
-      if (lane == 0 && fh == 0) {
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) sacc[S::R_BO + o] += accbo[o];
       }
     }
-    __syncthreads();
+    if (lane < 16) {
+      const int row = f0 + lane;
+#pragma unroll
+      for (int l = 2; l <= L; ++l) mine[S::R_H + (l - 2) * S::R_HSTRIDE + row] = accb[l - 1];
+      mine[S::R_B1 + row] = accb[0];
+#pragma unroll
+      for (int dd = 0; dd < DIN; ++dd) mine[S::R_W1 + row * DIN + dd] = accW1[dd];
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) mine[S::R_WO + o * kHid + row] = accWo[o];
+    }
+    if (lane == 0 && fh == 0) {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) mine[S::R_BO + o] = accbo[o];
+    }
   }
-  float* dst = a.partial[blockIdx.z] + ((size_t)blockIdx.x * a.P + p) * net.total;
+  __syncthreads();
+  float* sacc = sall + kWarps * S::R_PAD;          // the summed vector, after the per-warp copies
+  for (int i = tid; i < S::R_END; i += kThreads) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) sum += sall[w * S::R_PAD + i];
+    sacc[i] = sum;
+  }
+  __syncthreads();
+  float* dst = a.partial[zn] + ((size_t)slot * a.P + p) * net.total;
   const int base = net.off_b[0];
   for (int i = tid; i < net.total; i += kThreads) {
     const int g = base + i;
@@ -469,7 +494,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a) {
     dst[i] = sacc[src];
   }
   fence_before_sync();
-  __syncthreads();
+  __syncthreads();               // the next segment restages the weights and reuses the tiles the reduction aliased
+  fence_after_sync();
+  }  // segments
   if (warp == 0) tmem_dealloc<512>(tmem_base_s);
 }
 
@@ -480,9 +507,13 @@ int launch_tc_bwd(const MlpArgs& a, int chunks, int nets, cudaStream_t st) {
   // wide input / output layers (d > 2 together with out > 2 ...) do not leave room for three warpgroups of transposed
   // tiles in the 227 KB of shared memory: those shapes run on the CUDA-core kernel (mlp.cu)
   if (smem + 256 > 227 * 1024) return launch_mlp_fast(a, nets, chunks, true, st);
+  int grid = 0, per_cta = 0;
+  if (mlp_tc_bwd_slots(a.P, nets, a.T * a.n, &grid, &per_cta) > chunks) return PACOH_ERR_WORKSPACE;   // partial slots
+  // unused slots of the partial buffers must read as zero in the fixed-order reduction
+  for (int z = 0; z < nets; ++z)
+    PACOH_CUDA_CHECK(cudaMemsetAsync(a.partial[z], 0, sizeof(float) * (size_t)chunks * a.P * a.net[z].total, st));
   PACOH_CUDA_CHECK(cudaFuncSetAttribute(mlp_tc_bwd_kernel<L, DIN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(chunks, a.P, nets);
-  mlp_tc_bwd_kernel<L, DIN, OUT><<<grid, kThreads, smem, st>>>(a);
+  mlp_tc_bwd_kernel<L, DIN, OUT><<<grid, kThreads, smem, st>>>(a, nets, per_cta);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }
@@ -510,6 +541,43 @@ int bwd_dispatch_din(const MlpArgs& a, int din_pad, int out_pad, int chunks, int
 int bwd_pad_pow2(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : 4); }
 
 }  // namespace
+
+// Persistent schedule of the tensor-core backward kernel: one CTA per SM, the nets * P * tiles tile space cut into equal
+// ranges.  Returns the number of partial-gradient slots a (net, particle) can be split into (= CTAs touching it), which
+// sizes the (slots, P, D_net) partial buffers.
+int mlp_tc_bwd_slots(int P, int nets, int Q, int* grid_out, int* per_cta_out) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    else { sms = 148; cudaGetLastError(); }
+  }
+  // One CTA per SM would be ideal for the schedule, but a warpgroup sums ALL its tiles into one fp32 TMEM accumulator:
+  // measured on config #4 (tools/fullsize_fp64_check.py), 461 tiles per accumulator leave 6e-5 relative error in the
+  // weight gradients, 115 tiles 1.7e-5.  So the launch is cut into `waves` equal CTAs per SM such that no warpgroup
+  // accumulates more than kBwdMaxTilesPerAcc tiles (each extra wave costs ~18 us of CTA start / reduction time).
+  static int waves_env = -1;
+  if (waves_env < 0) {
+    const char* e = getenv("PACOH_BWD_WAVES");
+    waves_env = e != nullptr && atoi(e) > 0 ? atoi(e) : 0;
+  }
+  const long long tiles = (Q + kTile - 1) / kTile, total = (long long)nets * P * tiles;
+  const long long per1 = (total + sms - 1) / sms;
+  long long waves = waves_env > 0 ? waves_env : (per1 + kWG * kBwdMaxTilesPerAcc - 1) / (kWG * kBwdMaxTilesPerAcc);
+  if (waves < 1) waves = 1;
+  const long long ctas = (long long)sms * waves;
+  long long per = (total + ctas - 1) / ctas;
+  if (per < 6) per = 6;          // at least two tiles per warpgroup: below that the fixed per-CTA cost dominates
+  const int grid = (int)((total + per - 1) / per);
+  int slots = 1;
+  for (long long pn = 0; pn < (long long)nets * P; ++pn) {
+    const int segs = (int)(((pn + 1) * tiles - 1) / per - (pn * tiles) / per + 1);
+    slots = segs > slots ? segs : slots;
+  }
+  if (grid_out) *grid_out = grid;
+  if (per_cta_out) *per_cta_out = (int)per;
+  return slots;
+}
 
 // Backward pass of the `nets` nets in a.net[] (same depth <= 3, widths <= 32, d <= 4, out <= 4) on tcgen05 + CUDA cores.
 int launch_mlp_tc_bwd(const MlpArgs& a, int nets, int chunks, cudaStream_t st) {

@@ -286,7 +286,8 @@ def test_full_size_deterministic_and_sharding_is_linear(eng, config4):
         _, pk, _ = c["e"].mll_fwd_bwd(c["theta"], tidx[s * 1024:(s + 1) * 1024].contiguous())
         acc += pk.double()
     scale = packed_a.abs().max().item()
-    assert (acc - packed_a.double()).abs().max().item() <= 2e-5 * scale
+    # two fp32 evaluation orders of a 204800-point sum: half the parity bar (the fp64 check below is the real one)
+    assert (acc - packed_a.double()).abs().max().item() <= 5e-5 * scale
     # per-task values do not depend on the batch they are evaluated in
     mll_s, _, _ = c["e"].mll_fwd_bwd(c["theta"], tidx[:1024].contiguous())
     assert torch.equal(mll_s, mll_a[:, :1024])
@@ -311,6 +312,26 @@ def test_full_size_spot_check_against_oracle(eng, config4):
     _, logp64, g64 = oracle64(c["lay"], c["x"], c["y"], c["theta"][:P8].cpu().numpy(), sub)
     assert relmax(logp, logp64) <= RTOL
     assert_groups(c["arch"], score, g64)
+
+
+def test_full_size_gradient_against_fp64_oracle(eng, config4):
+    """The whole 64 x 4096 x 50 batch through the kernels (so every accumulator sees its real length: the weight
+    gradients are summed over 204800 points per particle) against the fp64 oracle for three of the particles."""
+    c = config4
+    P, D, K = c["P"], c["lay"].D, 3
+    _, packed, info = c["e"].mll_fwd_bwd(c["theta"], torch.from_numpy(c["idx"]).to(DEV))
+    assert int(info.max()) == 0
+    g = packed[:P * D].view(P, D).cpu().double()
+    msum = packed[P * D:].cpu().double()
+    th64 = c["theta"][:K].cpu().double().requires_grad_(True)
+    xs, ys = torch.from_numpy(c["x"]).double(), torch.from_numpy(c["y"]).double()
+    tot = torch.zeros(K, dtype=torch.float64)
+    for t in c["idx"]:
+        tot = tot + orc.task_mll(th64, c["lay"], xs[t], ys[t])
+    tot.sum().backward()
+    assert ((msum[:K] - tot.detach()).abs() / tot.detach().abs()).max().item() <= RTOL
+    for k in range(K):
+        assert (g[k] - th64.grad[k]).abs().max().item() <= 0.5 * RTOL * th64.grad[k].abs().max().item()
 
 
 def test_full_size_svgd_direction_properties(eng, config4):

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a, int 
     }
   };
 
+  if (wg > 0) __nanosleep(2000u * wg);   // stagger the three tile pipelines by ~1/3 tile: they start in lockstep otherwise
   for (int tile = t0 + wg; tile < t1; tile += kWG) {
     float x[DIN], dr[OUT];
 #pragma unroll

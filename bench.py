@@ -172,6 +172,9 @@ def run_ours(args):
     model = GPRegressionMetaLearnedSVGD(data, num_particles=P, random_seed=30)
     if world > 1:
         model.shard_tasks()
+    collective = ("none (single GPU)" if world == 1 else
+                  "all-reduce fused into the finalize kernel over NVLink peer memory (pacoh_peer_allreduce_finalize)" if model._peer is not None
+                  else "NCCL all-reduce of the packed (P, D+1) buffer (peer memory unavailable: %s)" % getattr(model, "_peer_error", None))
 
     def barrier():
         if world > 1:
@@ -302,7 +305,7 @@ def run_ours(args):
     launches_per_step = 3 + 3 + 1 + 3 + 1      # mlp_fwd, gp_mll, mlp_bwd | 2 partial reductions + hyp reduction | finalize | svgd x3 | adam
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(world),
+            "data": "synthetic", "config": dict(config_dict(world), collective=collective),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms.item() / e2e_steps, "timing": "host wall clock around K steps (2-deep pipelined: batch k+1 is gathered on the host while step k runs; every step copies its batch H2D from pinned memory and its logp D2H), barrier + synchronize on both sides"},
             "gpu_launches": launches_per_step * args.steps, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}

@@ -116,6 +116,23 @@ int pacoh_logprob_finalize(int32_t P, int64_t D, const float* theta, const float
                            void* stream);
 
 /*
+ * Task-sharded runs (one process per GPU of an NVLink / NVSwitch node): pacoh_logprob_finalize with the all-reduce of
+ * the packed likelihood buffer (dtheta_lik (P, D) | mll_sum (P), P*D + P floats) FUSED in, over peer memory instead of
+ * an NCCL launch.  peer_bufs[r] / peer_flags[r] (host arrays of `world` device pointers, world <= PACOH_MAX_PEERS) are
+ * rank r's packed buffer for this step and rank r's flag array (>= world uint32, zero-initialised once), both in
+ * memory every rank of the node has mapped (CUDA IPC / symmetric memory).  `token` must increase by one per call on
+ * every rank (start at 1) and the caller must alternate between two packed buffers (token parity): rank r's kernel
+ * releases `token` into slot r of every peer's flags, acquires all of its own slots, then sums the `world` buffers in
+ * rank order (bitwise identical on all ranks) while applying prior and pre_factor exactly like pacoh_logprob_finalize.
+ * Replaces the autograd accumulation over the per-task loop of random_gp.py:200-222 across devices.
+ */
+#define PACOH_MAX_PEERS 8
+int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const void* const* peer_bufs, void* const* peer_flags,
+                                  uint32_t token, int32_t P, int64_t D, const float* theta, const float* prior_mu,
+                                  const float* prior_sigma, float prior_factor, float pre_factor, float* logp,
+                                  float* dtheta, void* stream);
+
+/*
  * SVGD direction (SVGD.phi tail + RBF_Kernel, svgd.py:18-21,32-59,103-107):
  *   d2_ij = |theta_i|^2 + |theta_j|^2 - 2 theta_i.theta_j ;  gamma = 1/(1e-8 + 2 h^2)
  *   bandwidth h > 0 fixed, or h <= 0: median heuristic  h^2 = median(d2 over all P*P) / (2 log(P+1))

@@ -75,6 +75,73 @@ __global__ void logprob_finalize_kernel(int P, int64_t D, const float* __restric
   }
 }
 
+// ---- all-reduce over NVLink peer memory FUSED into the finalize step (task-sharded runs) ---------------------------
+// Every rank's packed likelihood buffer (dtheta_lik (P, D) | mll_sum (P)) lives in symmetric memory that all ranks of
+// the node have mapped.  One kernel per rank: announce "my buffer for step `token` is complete" by writing the token
+// into slot `rank` of every peer's flag array (system-scope release), wait until every peer has announced to us
+// (acquire), then read all `world` buffers directly over NVLink, sum them in rank order (bitwise identical on every
+// rank) and apply the hyper-prior / pre-factor on the fly.  No NCCL launch, no extra pass over the data; the buffers are
+// double-buffered by step parity on the host side, which together with the monotone tokens makes reuse safe.
+struct PeerPtrs {
+  const float* buf[PACOH_MAX_PEERS];
+  unsigned int* flag[PACOH_MAX_PEERS];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {      // peer data: never through the (incoherent) L1
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__global__ void peer_sum_finalize_kernel(PeerPtrs pp, int world, int rank, unsigned int token, int P, int64_t D,
+                                         const float* __restrict__ theta, const float* __restrict__ mu,
+                                         const float* __restrict__ sigma, float prior_factor, float pre_factor,
+                                         float* __restrict__ logp, float* __restrict__ dtheta) {
+  __shared__ float red[32];
+  if (threadIdx.x < world) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();                                     // the kernels before us on this stream wrote the buffer
+      st_release_sys(pp.flag[threadIdx.x] + rank, token);
+    }
+    while ((int)(ld_acquire_sys(pp.flag[rank] + threadIdx.x) - token) < 0) { }
+  }
+  __syncthreads();
+  const int p = blockIdx.x;
+  float lp = 0.0f;
+  for (int64_t k = threadIdx.x; k < D; k += blockDim.x) {
+    float v[PACOH_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < PACOH_MAX_PEERS; ++r) v[r] = r < world ? ld_peer(pp.buf[r] + p * D + k) : 0.0f;   // all in flight
+    float dl = v[0];
+#pragma unroll
+    for (int r = 1; r < PACOH_MAX_PEERS; ++r) dl += v[r];                                                  // rank order
+    const float s = sigma[k];
+    const float zc = (theta[p * D + k] - mu[k]) / s;
+    lp += -0.5f * zc * zc - logf(s) - 0.91893853320467274178f;
+    dtheta[p * D + k] = fmaf(pre_factor, dl, -prior_factor * zc / s);
+  }
+  lp = warp_sum(lp);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      float ms = 0.0f;
+      for (int r = 0; r < world; ++r) ms += ld_peer(pp.buf[r] + (int64_t)P * D + p);
+      logp[p] = fmaf(prior_factor, v, pre_factor * ms);
+    }
+  }
+}
+
 __global__ void vi_sample_kernel(int S, int64_t D, const float* __restrict__ loc, const float* __restrict__ scale,
                                  const float* __restrict__ eps, float* __restrict__ theta, float* __restrict__ logq) {
   __shared__ float red[32];
@@ -155,6 +222,27 @@ extern "C" int pacoh_logprob_finalize(int32_t P, int64_t D, const float* theta, 
   }
   logprob_finalize_kernel<<<P, 256, 0, (cudaStream_t)stream>>>(P, D, theta, prior_mu, prior_sigma, prior_factor, pre_factor,
                                                                mll_sum, dtheta_lik, logp, dtheta);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const void* const* peer_bufs, void* const* peer_flags,
+                                             uint32_t token, int32_t P, int64_t D, const float* theta, const float* prior_mu,
+                                             const float* prior_sigma, float prior_factor, float pre_factor, float* logp,
+                                             float* dtheta, void* stream) {
+  if (world < 1 || world > PACOH_MAX_PEERS || rank < 0 || rank >= world || !peer_bufs || !peer_flags || P < 1 || D < 1 ||
+      !theta || !prior_mu || !prior_sigma || !logp || !dtheta) {
+    set_error("pacoh_peer_allreduce_finalize: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  PeerPtrs pp;
+  for (int r = 0; r < PACOH_MAX_PEERS; ++r) {
+    pp.buf[r] = r < world ? (const float*)peer_bufs[r] : nullptr;
+    pp.flag[r] = r < world ? (unsigned int*)peer_flags[r] : nullptr;
+    if (r < world && (!pp.buf[r] || !pp.flag[r])) { set_error("pacoh_peer_allreduce_finalize: null peer pointer"); return PACOH_ERR_INVALID; }
+  }
+  peer_sum_finalize_kernel<<<P, 1024, 0, (cudaStream_t)stream>>>(pp, world, rank, token, P, D, theta, prior_mu, prior_sigma,
+                                                                prior_factor, pre_factor, logp, dtheta);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

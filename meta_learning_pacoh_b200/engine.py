@@ -212,9 +212,62 @@ def logprob_finalize(theta, prior_mu, prior_sigma, prior_factor, pre, packed, wa
     return logp, dtheta
 
 
-def meta_log_prob_and_score(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None):
+class PeerAllReduce:
+    """All-reduce of the packed (P*D + P) likelihood buffer over NVLink peer memory, fused into the finalize kernel
+    (pacoh_peer_allreduce_finalize) -- the task-sharded replacement for ``all_reduce`` + ``logprob_finalize``.
+
+    Every rank allocates [2 x packed | flags] in torch symmetric memory (CUDA IPC / fabric handles under the hood) and
+    exchanges the mappings once (collective).  Per step the MLL kernels write this rank's partial sums straight into
+    the buffer of the step's parity; one kernel then announces / waits through the flags and reads all ranks' buffers.
+    Construction raises if symmetric memory is unavailable for the group (callers fall back to NCCL)."""
+
+    def __init__(self, group, P, D, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.P, self.D, self.device = int(P), int(D), torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError("peer all-reduce supports at most %d ranks" % _lib.MAX_PEERS)
+        self.n = self.P * self.D + self.P
+        self.n_pad = (self.n + 63) // 64 * 64
+        total = 2 * self.n_pad + 64                      # two parities, then the flag words (uint32 stored in float slots)
+        self.local = symm.empty(total, dtype=torch.float32, device=self.device)
+        self.local.zero_()
+        self.handle = symm.rendezvous(self.local, group)
+        bases = [self.handle.get_buffer(r, (total,), torch.float32).data_ptr() for r in range(self.world)]
+        self._bufs = [(ctypes.c_void_p * self.world)(*[b + 4 * h * self.n_pad for b in bases]) for h in range(2)]
+        self._flags = (ctypes.c_void_p * self.world)(*[b + 4 * 2 * self.n_pad for b in bases])
+        self.token = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                              # every rank's flags are zero before anyone announces
+
+    def out_buffer(self):
+        """The packed buffer the NEXT finalize() will sum (pass it as ``out=`` to MetaMLLEngine.mll_fwd_bwd)."""
+        h = (self.token + 1) & 1
+        return self.local[h * self.n_pad:h * self.n_pad + self.n]
+
+    def finalize(self, theta, prior_mu, prior_sigma, prior_factor, pre):
+        self.token += 1
+        h = self.token & 1
+        P, D = theta.shape
+        assert (P, D) == (self.P, self.D)
+        logp = torch.empty(P, dtype=torch.float32, device=self.device)
+        dtheta = torch.empty(P, D, dtype=torch.float32, device=self.device)
+        check(lib.pacoh_peer_allreduce_finalize(self.world, self.rank, self._bufs[h], self._flags, self.token & 0xFFFFFFFF, P, D,
+                                                _ptr(theta), _ptr(prior_mu), _ptr(prior_sigma), float(prior_factor), float(pre),
+                                                _ptr(logp), _ptr(dtheta), _stream()))
+        return logp, dtheta
+
+
+def meta_log_prob_and_score(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None, peer=None):
     """(logp (P,), score = d logp / d theta (P, D), info) without autograd: what SVGD.phi needs (svgd.py:13-16).
-    ``task_idx`` is this rank's shard when ``group`` is given; ``pre`` is computed from the GLOBAL batch."""
+    ``task_idx`` is this rank's shard when ``group`` is given; ``pre`` is computed from the GLOBAL batch.  With a
+    ``PeerAllReduce`` the cross-rank sum runs over NVLink peer memory inside the finalize kernel, else as one NCCL
+    all-reduce of the packed buffer."""
+    if peer is not None:
+        _, _, info = engine.mll_fwd_bwd(theta, task_idx, want_mll=False, want_info=True, out=peer.out_buffer())
+        logp, dtheta = peer.finalize(theta, prior_mu, prior_sigma, prior_factor, pre)
+        return logp, dtheta, info
     _, packed, info = engine.mll_fwd_bwd(theta, task_idx, want_mll=False, want_info=True)
     if group is not None:
         torch.distributed.all_reduce(packed, group=group)

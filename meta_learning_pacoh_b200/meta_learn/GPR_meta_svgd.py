@@ -5,6 +5,7 @@ meta_learn/GPR_meta_svgd.py:14-235 (GPRegressionMetaLearnedSVGD), with the per-t
     pacoh_meta_mll_fwd_bwd  ->  [NCCL all-reduce when task-sharded]  ->  pacoh_logprob_finalize
     pacoh_svgd_phi          ->  pacoh_adam_step
 """
+import os
 import time
 
 import numpy as np
@@ -51,7 +52,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         X, Y = self._build_task_dicts(meta_train_data)
         self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
         self._idx_host = torch.empty(self.task_batch_size, dtype=torch.int32).pin_memory()
-        self._group = None
+        self._group, self._peer = None, None
         self._rank, self._world = 0, 1
         self.fitted = False
 
@@ -64,6 +65,19 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         assert dist.is_initialized()
         self._group = group if group is not None else dist.group.WORLD
         self._rank, self._world = dist.get_rank(self._group), dist.get_world_size(self._group)
+        # cross-rank sum fused into the finalize kernel over NVLink peer memory (engine.PeerAllReduce); NCCL all-reduce
+        # when symmetric memory is unavailable for this group or PACOH_ALLREDUCE=nccl asks for it (A/B measurements)
+        self._peer, self._peer_error = None, None
+        if self._world > 1 and os.environ.get("PACOH_ALLREDUCE", "peer") != "nccl":
+            ok = torch.zeros(1, device=self.device)
+            try:
+                self._peer = eng.PeerAllReduce(self._group, self.num_particles, self.arch.D, self.device)
+                ok += 1
+            except Exception as e:   # noqa: BLE001  (any failure to map peer memory: fall back on every rank)
+                self._peer_error = repr(e)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
+            if ok.item() < 1:
+                self._peer = None
         return self
 
     # ------------------------------------------------------------------ training
@@ -102,7 +116,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         pre = eng.pre_factor([self.engine.n] * T)                      # GLOBAL batch (random_gp.py:209-212)
         self._phi.prepare(self.particles)                              # K(theta) on a side stream, under the MLL kernels
         logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
-                                                        self._prior_sigma, self.prior_factor, pre, self._group)
+                                                        self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
         phi = self._phi(self.particles, score)
         if isinstance(self.optimizer, eng.PacohAdam):
             self.optimizer.step(direction=phi)                         # grad = -phi (svgd.py:27)
@@ -159,7 +173,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         pre = eng.pre_factor([se.n] * T)
         self._phi.prepare(self.particles)
         logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx[slot], self._prior_mu,
-                                                        self._prior_sigma, self.prior_factor, pre, self._group)
+                                                        self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
         phi = self._phi(self.particles, score)
         if isinstance(self.optimizer, eng.PacohAdam):
             self.optimizer.step(direction=phi)

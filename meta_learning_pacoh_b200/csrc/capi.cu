@@ -170,6 +170,30 @@ static int make_plan(const pacoh_arch_t* arch, int P, int T, int n, Plan* pl) {
   return PACOH_OK;
 }
 
+// ---- side stream for work that can run next to the MLP backward (created lazily, one per process / device in use)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t after_gp = nullptr, hyp_done = nullptr;
+  int device = -1;
+};
+static SideStream g_side;
+
+static bool side_stream_ready() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (g_side.stream != nullptr && g_side.device == dev) return true;
+  if (g_side.stream != nullptr) return false;            // library already bound to another device: stay on one stream
+  if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_side.after_gp, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_side.hyp_done, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    g_side.stream = nullptr;
+    return false;
+  }
+  g_side.device = dev;
+  return true;
+}
+
 // ---- optional per-stage timing (bench.py roofline): events are created lazily and reused
 struct StageTimer {
   bool on = false;
@@ -338,12 +362,23 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
   if ((rc = launch_gp_mll(ga, st)) != PACOH_OK) { if (rc == PACOH_ERR_UNSUPPORTED) set_error("GP kernel: unsupported n=%d / F=%d", n, m.F); return rc; }
 
   stage_mark(2, st);
+  // The (P, T) -> (P) reduction of the per-task values and hyper-parameter gradients only needs the GP kernel's output
+  // and writes columns of dtheta_lik the MLP reductions do not touch: when there is an MLP backward to hide it under, it
+  // runs on a side stream next to it and is joined at the end.
+  const bool overlap_hyp = (pl.mean_nn || pl.kern_nn) && side_stream_ready();
+  if (overlap_hyp) {
+    PACOH_CUDA_CHECK(cudaEventRecord(g_side.after_gp, st));
+    PACOH_CUDA_CHECK(cudaStreamWaitEvent(g_side.stream, g_side.after_gp, 0));
+    if ((rc = launch_reduce_hyp(ga, dtheta_lik, mll_sum, g_side.stream)) != PACOH_OK) return rc;
+    PACOH_CUDA_CHECK(cudaEventRecord(g_side.hyp_done, g_side.stream));
+  }
   if ((rc = run_mlp(true)) != PACOH_OK) return rc;
   stage_mark(3, st);
 
   if (pl.mean_nn && (rc = launch_reduce_partials(ws + pl.off_pmean, pl.chunks, P, m.mean.total, dtheta_lik, m.D, m.mean.off_b[0], st)) != PACOH_OK) return rc;
   if (pl.kern_nn && (rc = launch_reduce_partials(ws + pl.off_pkern, pl.chunks, P, m.kern.total, dtheta_lik, m.D, m.kern.off_b[0], st)) != PACOH_OK) return rc;
-  rc = launch_reduce_hyp(ga, dtheta_lik, mll_sum, st);
+  if (overlap_hyp) PACOH_CUDA_CHECK(cudaStreamWaitEvent(st, g_side.hyp_done, 0));
+  else rc = launch_reduce_hyp(ga, dtheta_lik, mll_sum, st);
   stage_mark(4, st);
   return rc;
 }

@@ -554,7 +554,7 @@ int mlp_tc_bwd_slots(int P, int nets, int Q, int* grid_out, int* per_cta_out) {
     else { sms = 148; cudaGetLastError(); }
   }
   // One CTA per SM would be ideal for the schedule, but a warpgroup sums ALL its tiles into one fp32 TMEM accumulator:
-  // measured on config #4 (tools/fullsize_fp64_check.py), 461 tiles per accumulator leave 6e-5 relative error in the
+  // measured on config #4 (tests/manual/fullsize_fp64_check.py), 461 tiles per accumulator leave 6e-5 relative error in the
   // weight gradients, 115 tiles 1.7e-5.  So the launch is cut into `waves` equal CTAs per SM such that no warpgroup
   // accumulates more than kBwdMaxTilesPerAcc tiles (each extra wave costs ~18 us of CTA start / reduction time).
   static int waves_env = -1;

@@ -1,8 +1,8 @@
 """Config #4 (64 x 4096 x 50) gradient of the summed MLL against the fp64 oracle for a few particles (the CPU oracle
-loops over tasks: ~1 min).  Run on a GPU box: python tools/fullsize_fp64_check.py [n_particles_checked]"""
+loops over tasks: ~1 min).  Run on a GPU box: python tests/manual/fullsize_fp64_check.py [n_particles_checked]"""
 import os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pacoh_oracle as orc
 from meta_learning_pacoh_b200 import engine as eng
 P, T, n = 64, 4096, 50

@@ -1,8 +1,8 @@
 """Full-size (config #4) self-consistency of the gradient: sum over 4 task shards vs the whole batch, relative to max |g|.
-Run on a GPU box: python tools/linearity_check.py"""
+Run on a GPU box: python tests/manual/linearity_check.py"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pacoh_oracle as orc
 from meta_learning_pacoh_b200 import engine as eng
 P, T, n = 64, 4096, 50

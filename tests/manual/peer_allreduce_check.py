@@ -1,9 +1,9 @@
 """Validation of the peer-memory all-reduce fused into the finalize kernel (engine.PeerAllReduce) against the NCCL path.
 Run under torchrun on >= 2 GPUs of one node:
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/peer_allreduce_check.py"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/manual/peer_allreduce_check.py"""
 import os, sys, time
 import numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import pacoh_oracle as orc
 from meta_learning_pacoh_b200 import engine as eng
 

@@ -39,15 +39,31 @@ for it in range(6):
     if rank == 0:
         print("iter %d: peer vs nccl rel diff %.2e, identical across ranks: %s" % (it, err, same))
     assert same
-# latency
-torch.cuda.synchronize(); dist.barrier()
-for name, pr in (("nccl", None), ("peer", peer)):
-    t0 = time.perf_counter()
-    for _ in range(50):
-        eng.meta_log_prob_and_score(theta, e, shard, mu, sigma, 0.01, pre, group=dist.group.WORLD, peer=pr)
+# latency of the cross-rank sum + finalize alone, at the config #4 buffer size (64 x 2342 + 64 floats), CUDA events
+P4 = 64
+peer4 = eng.PeerAllReduce(dist.group.WORLD, P4, lay.D, dev)
+theta4 = (mu.cpu() + sigma.cpu() * torch.randn(P4, lay.D, generator=torch.Generator().manual_seed(1))).to(dev)
+packed4 = torch.randn(P4 * lay.D + P4, device=dev)
+def run_nccl():
+    buf = packed4.clone()
+    dist.all_reduce(buf)
+    return eng.logprob_finalize(theta4, mu, sigma, 0.01, 0.5, buf)
+def run_peer():
+    peer4.out_buffer().copy_(packed4)
+    return peer4.finalize(theta4, mu, sigma, 0.01, 0.5)
+for name, fn in (("nccl all_reduce + pacoh_logprob_finalize", run_nccl), ("pacoh_peer_allreduce_finalize", run_peer)):
+    for _ in range(10):
+        fn()
     torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 200 * 1e3], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("%s path: %.1f us per call (MLL kernels included)" % (name, (time.perf_counter() - t0) / 50 * 1e6))
+        print("%-44s %.1f us per step (incl. a %d-float device copy), world %d" % (name, t.item(), packed4.numel(), world))
 if rank == 0:
     print("OK" if worst <= 1e-6 else "MISMATCH", worst)
 dist.destroy_process_group()

@@ -8,7 +8,7 @@ Workload (config.workload): BASELINE configs[3], the configuration the metric an
 on -- PACOH-SVGD, 64 particles x 4096 synthetic sinusoid tasks x 50 points, (32,32) mean and kernel nets, F = 2; it fits
 one GPU.  One "step" = one full SVGD meta-training step on one sampled batch of T = 4096 tasks (with replacement):
 batched MLL forward+backward for all 64 x 4096 (particle, task) pairs, hyper-prior, SVGD direction with the median
-heuristic, Adam update.  For N > 1 the same global batch is task-sharded over the ranks (strong scaling) with one NCCL
+heuristic, Adam update.  For N > 1 the same global batch is task-sharded over the ranks (strong scaling) with one cross-rank
 all-reduce of the packed (P, D+1) gradient buffer per step.  One eval = one (particle, task) MLL value + its gradient.
 """
 import argparse

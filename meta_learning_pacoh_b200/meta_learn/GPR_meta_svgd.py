@@ -2,7 +2,7 @@
 meta_learn/GPR_meta_svgd.py:14-235 (GPRegressionMetaLearnedSVGD), with the per-task / per-particle Python loops
 (random_gp.py:214-217, svgd.py:12-28) replaced by three C-ABI calls per step:
 
-    pacoh_meta_mll_fwd_bwd  ->  [NCCL all-reduce when task-sharded]  ->  pacoh_logprob_finalize
+    pacoh_meta_mll_fwd_bwd  ->  pacoh_logprob_finalize   [task-sharded: pacoh_peer_allreduce_finalize, or NCCL + finalize]
     pacoh_svgd_phi          ->  pacoh_adam_step
 """
 import os
@@ -60,7 +60,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
     def shard_tasks(self, group=None):
         """Task-shard the sampled batch over the ranks of ``group`` (default: the world group).  Every rank must be
         constructed with the same data and seed: all ranks then draw the same batch indices, evaluate a contiguous
-        slice of them, and one NCCL all-reduce of the packed (P, D+1) likelihood buffer restores the full sums."""
+        slice of them, and one cross-rank sum of the packed (P, D+1) likelihood buffer restores the full sums."""
         import torch.distributed as dist
         assert dist.is_initialized()
         self._group = group if group is not None else dist.group.WORLD

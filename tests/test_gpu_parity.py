@@ -224,13 +224,14 @@ def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
     assert_groups(arch, got, g_ref.numpy().reshape(1, -1), tol=2e-4)
 
 
-def test_jitter_ladder_and_not_psd_reporting(eng):
+@pytest.mark.parametrize("n", [8, 40])      # register kernel / tensor-memory kernel (two matrices per CTA retry together)
+def test_jitter_ladder_and_not_psd_reporting(eng, n):
     """duplicate inputs + vanishing noise: singular K.  The kernel must climb the 1e-6/1e-5/1e-4 jitter ladder
     (gpytorch psd_safe_cholesky) or report failure; the host wrapper raises NotPSDError on failure."""
     arch = eng.GPArch(1, mean_kind="zero", covar_kind="SE")
-    x = np.zeros((2, 8, 1), np.float32)             # all points identical -> rank-1 Gram
-    x[1] = np.linspace(-1, 1, 8, dtype=np.float32).reshape(8, 1)
-    y = np.ones((2, 8), np.float32)
+    x = np.zeros((2, n, 1), np.float32)             # all points identical -> rank-1 Gram
+    x[1] = np.linspace(-1, 1, n, dtype=np.float32).reshape(n, 1)
+    y = np.ones((2, n), np.float32)
     theta = np.zeros((2, arch.D), np.float32)
     theta[0, arch.entries()["noise_raw"][0]] = -40.0      # softplus(-40) ~ 4e-18
     theta[1, arch.entries()["noise_raw"][0]] = 0.0
@@ -244,6 +245,11 @@ def test_jitter_ladder_and_not_psd_reporting(eng):
             eng.check_info(torch.from_numpy(info))
     else:
         assert np.isfinite(mll.cpu().numpy()).all()
+    # the healthy particle's values do not depend on the retries of the matrices it shares a launch / CTA with
+    mll1, packed1, info1 = e.mll_fwd_bwd(torch.from_numpy(theta[1:2]).to(DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))
+    assert torch.equal(mll1[0], mll[1]) and int(info1.abs().max()) == 0
+    D = arch.D
+    assert torch.equal(packed1[:D], packed[D:2 * D])
 
 
 def test_unsupported_sizes_fail_loudly(eng):

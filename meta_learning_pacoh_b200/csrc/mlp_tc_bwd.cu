@@ -19,7 +19,7 @@
 // thread writes its point's column of dA_l^T / H_{l-1}^T straight into a SWIZZLE_128B K-major tile: a warp's 32 points
 // are one 128-byte swizzle row per feature (conflict-free column stores AND conflict-free lane-per-feature row reads),
 // one 8 KB K-block per warp.  The lo parts are STACKED under the values along M / N (rows 0-31: the unsplit fp32
-// value -- the tensor core truncates it to tf32 itself --, rows 32-63: value - tf32(value)), so ONE M128 N64 MMA per
+// value -- the tensor core truncates it to tf32 itself --, rows 32-63: value - tf32(value)), so ONE M64 N64 MMA per
 // 8 points yields hi*hi, hi*lo and lo*hi as separate 32x32 blocks of the accumulator (summed once per CTA):
 // 16 MMAs per tile instead of 48.  (Layout and truncation validated by tools/ubench/tc_sw128_test.cu.)
 // The dW MMAs are issued by a second thread and committed to their own mbarrier, so they overlap the dH round trip;
@@ -69,8 +69,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 template <int L, int DIN, int OUT>
 struct BwdSmem {
   static constexpr int LH = L > 1 ? L - 1 : 0;
-  // per-warpgroup stacked transposed tiles first (1024-byte aligned; the M = 128 MMA over-reads the 64-row dA^T tile
-  // by 8 row groups: that stays inside the warpgroup's H^T tile / the next warpgroup's tiles / the weights)
+  // per-warpgroup stacked transposed tiles first (1024-byte aligned)
   static constexpr int WG_TILES = (1 + LH) * kStackF;              // dA_l^T, then H_l^T for l = 1..L-1
   static constexpr int B = kWG * WG_TILES;                         // per layer l = 2..L: W hi, W lo, W^T hi, W^T lo (1024 floats each)
   static constexpr int W1 = B + LH * 4 * kHid * kHid;              // [32][DIN]
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a, int 
         gemm128x32x32_3xtf32_ts(tmem_u, bt_hi, bt_hi + kHid * kHid * 4, bar_u);          // dH_{l-1} = dA_l W_l
       } else if (wt == 32) {                        // a second issuer: the weight-gradient GEMM, on its own barrier
         fence_after_sync();
-        const uint32_t idesc = umma_idesc_tf32(128, 64);
+        const uint32_t idesc = umma_idesc_tf32(64, 64);   // M = 64: exactly the stacked rows, no over-read of the A tile
         const uint64_t da0 = umma_desc_sw128(at_u), db0 = umma_desc_sw128(at_u + (l - 1) * kStackF * 4);
 #pragma unroll
         for (int w = 0; w < 4; ++w)
@@ -437,16 +436,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a, int 
   __syncthreads();
   {
     float* mine = sall + warp * S::R_PAD;
-    if (L > 1 && fh == 0 && wq < 2) {   // dW_2 rows live in TMEM lanes 0-31 (hi*hi | hi*lo) and 32-63 (lo*hi) of every warpgroup
+    if (L > 1 && fh == 0) {
+      // M = 64 accumulator: row i of the stacked product sits in TMEM lane (i / 16) * 32 + i % 16 (probed by
+      // tools/ubench/tc_m64_probe.cu): quadrants 0, 1 hold the value rows j = 16 wq + lane (hi*hi | hi*lo), quadrants
+      // 2, 3 the lo rows j = 16 (wq - 2) + lane (lo*hi); lanes 16-31 of every quadrant are unused.
       uint32_t v[32];
-      tmem_ld32(lane_base + kTmemDW, v);
-      float* dstw = mine + S::R_H + kHid + lane * kHid;
+      tmem_ld32(lane_base + kTmemDW, v);                 // (.sync.aligned: the whole warp executes it)
+      const int j = 16 * (wq & 1) + lane;
+      float* dstw = mine + S::R_H + kHid + j * kHid;
+      if (lane < 16) {
 #pragma unroll
-      for (int k = 0; k < kHid; ++k) dstw[k] = __uint_as_float(v[k]);
-      if (wq == 0) {
+        for (int k = 0; k < kHid; ++k) dstw[k] = __uint_as_float(v[k]);
+      }
+      if (wq < 2) {
         tmem_ld32(lane_base + kTmemDW + 32, v);
+        if (lane < 16) {
 #pragma unroll
-        for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
+          for (int k = 0; k < kHid; ++k) dstw[k] += __uint_as_float(v[k]);
+        }
       }
     }
     if (lane < 16) {

@@ -284,10 +284,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_bwd_kernel(MlpArgs a, int 
     for (int j4 = 0; j4 < kFH; j4 += 4) {
       const float4 b = lds4(smem + S::B1 + f0 + j4);
       float acc[4] = {b.x, b.y, b.z, b.w};
+      float wv[4 * DIN];                            // the 4 features' first-layer weights: DIN vector loads, not 4 DIN scalar ones
+#pragma unroll
+      for (int qv = 0; qv < DIN; ++qv) {
+        const float4 t4 = lds4(smem + S::W1 + (f0 + j4) * DIN + 4 * qv);
+        wv[4 * qv] = t4.x; wv[4 * qv + 1] = t4.y; wv[4 * qv + 2] = t4.z; wv[4 * qv + 3] = t4.w;
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
 #pragma unroll
-        for (int dd = 0; dd < DIN; ++dd) acc[e] = fmaf(smem[S::W1 + (f0 + j4 + e) * DIN + dd], x[dd], acc[e]);
+        for (int dd = 0; dd < DIN; ++dd) acc[e] = fmaf(wv[e * DIN + dd], x[dd], acc[e]);
         h[j4 + e] = tanh_fast(acc[e]);
       }
     }

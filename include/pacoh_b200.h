@@ -139,6 +139,12 @@ int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const void* const
  *   phi = (K score + 2 gamma (rowsum(K) * theta - K theta)) / P
  * gamma_out (1 float, device) receives gamma.  workspace: pacoh_svgd_workspace_bytes(P, D).
  *
+ * kernel_kind PACOH_SVGD_IMQ (IMQSteinKernel(alpha=0.5, beta=-0.5), svgd.py:63-99, as GPR_meta_svgd.py:176-177 builds it):
+ *   K_ij = (alpha + sum_d (theta_jd - theta_id)^2 / h_d)^beta ;  bandwidth > 0: h_d = bandwidth, else
+ *   h_d = lower median over the pairs i < j of (theta_jd - theta_id)^2, divided by log(P+1)  (one on-device sort per d)
+ *   phi = (K score - d sum(K)/d theta) / P, the derivative taken like SVGD.phi takes it (first kernel argument only,
+ *   THROUGH the median: svgd.py:18-19).  gamma_out is set to 0.  P >= 2.
+ *
  * The kernel matrix depends on the particles only, not on the scores, so the call is also exposed in two stages:
  * pacoh_svgd_kernel_matrix (distances, median, K, row sums -> workspace, gamma) may run on a side stream WHILE the
  * batched MLL forward/backward computes the scores; pacoh_svgd_phi_apply then only contracts K with score / theta.

@@ -304,15 +304,17 @@ def meta_log_prob(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, 
 
 
 class SVGDDirection:
-    """phi = (K s + grad K) / P on device, median heuristic included (pacoh_svgd_phi; svgd.py:12-23, 32-59).
+    """phi = (K s + grad K) / P on device, median heuristic included (pacoh_svgd_phi; svgd.py:12-23, 32-99).
 
     ``prepare(theta)`` starts the score-independent half (pairwise distances, median bandwidth, K, row sums) on a side
     stream so that it overlaps the batched MLL forward/backward; the following ``__call__(theta, score)`` with the SAME
     particles then only waits for it and applies K.  Without ``prepare`` the call runs both halves in order."""
 
     def __init__(self, P, D, device, bandwidth=None, kernel="RBF"):
-        if kernel != "RBF":
-            raise NotImplementedError("only the RBF Stein kernel is implemented on the B200 path (IMQ: SURVEY 8(f).3)")
+        if kernel not in ("RBF", "IMQ"):
+            raise NotImplementedError("Stein kernel %r: only 'RBF' and 'IMQ' exist (GPR_meta_svgd.py:174-179)" % (kernel,))
+        # 'IMQ': IMQSteinKernel(alpha=0.5, beta=-0.5) with the per-dimension median bandwidth and the gradient through it
+        self.kind = _lib.SVGD_RBF if kernel == "RBF" else _lib.SVGD_IMQ
         self.P, self.D, self.device = P, D, torch.device(device)
         self.bandwidth = -1.0 if bandwidth is None else float(bandwidth)
         nbytes = check(lib.pacoh_svgd_workspace_bytes(P, D))
@@ -330,7 +332,7 @@ class SVGDDirection:
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)          # particles of the previous update are final; the last phi_apply is done with K
         with torch.cuda.stream(self._side):
-            check(lib.pacoh_svgd_kernel_matrix(self.P, self.D, _ptr(theta), self.bandwidth, _lib.SVGD_RBF, _ptr(self.gamma),
+            check(lib.pacoh_svgd_kernel_matrix(self.P, self.D, _ptr(theta), self.bandwidth, self.kind, _ptr(self.gamma),
                                                _ptr(self.ws), self.ws.numel(), _stream()))
             self._ready.record(self._side)
         self._prepared_for = (theta.data_ptr(), theta._version)
@@ -340,12 +342,12 @@ class SVGDDirection:
         phi = out if out is not None else torch.empty_like(theta)
         if self._prepared_for is not None and self._prepared_for == (theta.data_ptr(), theta._version):
             torch.cuda.current_stream(self.device).wait_event(self._ready)
-            check(lib.pacoh_svgd_phi_apply(self.P, self.D, _ptr(theta), _ptr(score), _lib.SVGD_RBF, _ptr(phi), _ptr(self.gamma),
+            check(lib.pacoh_svgd_phi_apply(self.P, self.D, _ptr(theta), _ptr(score), self.kind, _ptr(phi), _ptr(self.gamma),
                                            _ptr(self.ws), self.ws.numel(), _stream()))
         else:
             if self._prepared_for is not None:      # a stale prepare(): let it finish before the workspace is reused
                 torch.cuda.current_stream(self.device).wait_event(self._ready)
-            check(lib.pacoh_svgd_phi(self.P, self.D, _ptr(theta), _ptr(score), self.bandwidth, _lib.SVGD_RBF, _ptr(phi),
+            check(lib.pacoh_svgd_phi(self.P, self.D, _ptr(theta), _ptr(score), self.bandwidth, self.kind, _ptr(phi),
                                      _ptr(self.gamma), _ptr(self.ws), self.ws.numel(), _stream()))
         self._prepared_for = None
         return phi

@@ -245,6 +245,58 @@ def svgd_phi_autograd(theta, score, bandwidth=None):
     return (K.detach().matmul(score) + grad_K) / X.shape[0], gamma
 
 
+def imq_kernel_matrix(X, Y, alpha=0.5, beta=-0.5, bandwidth=None):
+    """IMQSteinKernel.forward (svgd.py:63-99): K_ij = (alpha + sum_d (X_jd - Y_id)^2 / h_d)^beta with, for
+    ``bandwidth=None``, h_d = median over the strict upper triangle {i < j} of (X_jd - Y_id)^2 (torch.median: the LOWER
+    median) divided by log(P + 1).  Differentiable in X, including through the median."""
+    ns = (X.unsqueeze(0) - Y.unsqueeze(1)) ** 2                       # [i, j, d]
+    if bandwidth is None:
+        P = ns.shape[0]
+        idx = torch.arange(P)
+        h = ns[idx > idx.unsqueeze(-1), ...].median(dim=0)[0] / math.log(P + 1)
+    else:
+        h = bandwidth
+    return torch.exp(beta * torch.log(alpha + torch.sum(ns / h, dim=-1)))
+
+
+def svgd_phi_imq_autograd(theta, score, bandwidth=None, alpha=0.5, beta=-0.5):
+    """svgd.py:18-21 verbatim structure with the IMQ kernel (autograd through the kernel AND its median bandwidth)."""
+    X = theta.detach().clone().requires_grad_(True)
+    K = imq_kernel_matrix(X, X.detach(), alpha, beta, bandwidth)
+    grad_K = -torch.autograd.grad(K.sum(), X)[0]
+    return (K.detach().matmul(score) + grad_K) / X.shape[0], K.detach()
+
+
+def svgd_phi_imq(theta, score, bandwidth=None, alpha=0.5, beta=-0.5):
+    """a11, IMQ closed form (what the CUDA kernels compute).  With ns_ijd = (x_jd - x_id)^2, base_ij = alpha + sum_d ns_ijd / h_d,
+    K = base^beta, A = beta base^(beta - 1):
+        d sum(K) / d x_md = (2 / h_d) sum_i A_im (x_md - x_id)                                   [direct]
+                          - [m == j*_d] (sum_ij A_ij ns_ijd / h_d^2) 2 (x_j*d - x_i*d) / log(P + 1)   [through the median]
+    where (i*_d < j*_d) is the pair whose squared distance is the (lower) median of dimension d; only the FIRST kernel
+    argument is differentiated (svgd.py:18: K(X, X.detach())), hence only x_j*.  phi = (K s - d sum(K)/dx) / P."""
+    X = theta.detach()
+    P, D = X.shape
+    ns = (X.unsqueeze(0) - X.unsqueeze(1)) ** 2                       # [i, j, d]
+    if bandwidth is None:
+        iu, ju = torch.triu_indices(P, P, offset=1)
+        vals = ns[iu, ju, :]                                          # (P(P-1)/2, D), row order = the reference's mask order
+        med, arg = vals.median(dim=0)
+        h = med / math.log(P + 1)
+        i_star, j_star = iu[arg], ju[arg]
+    else:
+        h = torch.full((D,), float(bandwidth), dtype=X.dtype)
+    base = alpha + (ns / h).sum(-1)
+    K = base ** beta
+    A = beta * base ** (beta - 1.0)
+    # direct term: m is the SECOND index of ns (the differentiated argument)
+    grad = (2.0 / h) * (A.sum(0).unsqueeze(1) * X - A.t().matmul(X))
+    if bandwidth is None:
+        c = torch.einsum("ij,ijd->d", A, ns) / h ** 2                 # -d sum(K) / d h_d
+        dd = torch.arange(D)
+        grad[j_star, dd] -= c * 2.0 * (X[j_star, dd] - X[i_star, dd]) / math.log(P + 1)
+    return (K.matmul(score) - grad) / P, K
+
+
 # --------------------------------------------------------------------------------------
 # a13: VI
 # --------------------------------------------------------------------------------------

@@ -84,6 +84,26 @@ def test_svgd_two_stage_direction_equals_single_call():
     assert torch.equal(sv(theta, score), ref)     # and without any prepare
 
 
+def test_svgd_imq_kernel_learner_steps(ml):
+    """kernel='IMQ' (GPR_meta_svgd.py:176-177): the learner trains, and its update equals the oracle's closed-form IMQ
+    direction applied to the engine's own score (the score path is checked elsewhere)."""
+    from meta_learning_pacoh_b200 import engine as eng
+    train, _ = orc.sinusoid_tasks(8, 5, seed=4, n_test=10)
+    m = ml.GPRegressionMetaLearnedSVGD(train, num_particles=6, kernel='IMQ', random_seed=3, num_iter_fit=4, optimizer='SGD', lr=1e-2)
+    before = m.particles.detach().clone()
+    idx = m._sample_task_indices()
+    pre = eng.pre_factor([m.engine.n] * len(idx))
+    _, score, _ = eng.meta_log_prob_and_score(before, m.engine, torch.from_numpy(np.asarray(idx, dtype=np.int32)).cuda(),
+                                              m._prior_mu, m._prior_sigma, m.prior_factor, pre)
+    m.svgd_step(idx)
+    phi, _ = orc.svgd_phi_imq(before.cpu().double(), score.cpu().double(), None)
+    expect = before.cpu().double() + 1e-2 * phi                      # SGD: particles += lr * phi  (grad = -phi)
+    got = m.particles.detach().cpu().double()
+    assert (got - expect).abs().max().item() <= 1e-4 * (1e-2 * phi.abs().max().item()) + 1e-7
+    m.meta_fit(verbose=False)
+    assert torch.isfinite(m.particles).all()
+
+
 def test_svgd_seed_determinism(ml):
     """tests/test_GPR.py:173-187 style: two runs with the same seed are bit-identical."""
     train, test = orc.sinusoid_tasks(12, 8, seed=3, n_test=20)

@@ -97,6 +97,31 @@ def test_svgd_phi_matches_reference_golden(eng, golden_dir, name, bw):
     assert relmax(phi.cpu().numpy(), fx["phi"]) <= RTOL
 
 
+@pytest.mark.parametrize("tag,name", [("cfg2", "svgd_cfg2.npz"), ("n20", "svgd_n20.npz")])
+@pytest.mark.parametrize("key,bw", [("median", None), ("bw", 0.7)])
+def test_svgd_phi_imq_matches_reference_golden(eng, golden_dir, tag, name, key, bw):
+    """kernel='IMQ' (IMQSteinKernel, svgd.py:63-99): per-dimension median bandwidth, gradient through the median."""
+    fx = np.load(os.path.join(golden_dir, name))
+    g = np.load(os.path.join(golden_dir, "svgd_imq.npz"))
+    P, D = fx["particles"].shape
+    sv = eng.SVGDDirection(P, D, DEV, bandwidth=bw, kernel="IMQ")
+    theta, score = torch.from_numpy(fx["particles"]).to(DEV), torch.from_numpy(fx["score"]).to(DEV)
+    phi = sv(theta, score)
+    assert relmax(phi.cpu().numpy(), g["phi_%s_%s" % (key, tag)]) <= RTOL
+    sv.prepare(theta)                                   # two-stage form gives the same
+    assert torch.equal(sv(theta, score), phi)
+
+
+def test_svgd_phi_imq_full_size_against_oracle(eng):
+    """64 particles x 2342 parameters (config #4's particle matrix): 2016 pairs per dimension through the on-device sort."""
+    g = torch.Generator().manual_seed(11)
+    theta = torch.randn(64, 2342, generator=g) * 0.5
+    score = torch.randn(64, 2342, generator=g)
+    phi = eng.SVGDDirection(64, 2342, DEV, kernel="IMQ")(theta.to(DEV), score.to(DEV))
+    ref, _ = orc.svgd_phi_imq(theta.double(), score.double(), None)
+    assert relmax(phi.cpu().numpy(), ref.numpy()) <= RTOL
+
+
 def test_vi_sample_and_gradient_match_reference_golden(eng, golden_dir):
     fx = np.load(os.path.join(golden_dir, "vi_cfg3.npz"))
     arch = eng.GPArch(1)
@@ -260,7 +285,7 @@ def test_unsupported_sizes_fail_loudly(eng):
     with pytest.raises(PacohError):
         e.mll_fwd_bwd(torch.zeros(2, arch.D, device=DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))
     with pytest.raises(NotImplementedError):
-        eng.SVGDDirection(4, 10, DEV, kernel="IMQ")
+        eng.SVGDDirection(4, 10, DEV, kernel="Matern")
 
 
 # ------------------------------------------------------------------------------------------ full-size properties

@@ -91,6 +91,18 @@ int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32_t T, int32
                            void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * The same for RAGGED task sets (tasks with different numbers of points, which the reference's per-task loop handles
+ * implicitly: random_gp.py:214-217): x / y are padded to n = max_t n_t rows per task and task_n (T_total) int32 holds
+ * every task's own n_t (1 <= n_t <= n).  Rows n_t .. n-1 of a task are ignored (any finite padding values), mll[p,t]
+ * is divided by n_t, and the padding rows receive exactly zero gradient.  task_n == NULL: all tasks have n points.
+ * The harmonic-mean pre_factor of random_gp.py:209-212 is the caller's (pacoh_logprob_finalize takes it as a scalar).
+ */
+int pacoh_meta_mll_fwd_bwd_ragged(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n,
+                                  const float* theta, const float* x, const float* y, const int32_t* task_n,
+                                  const int32_t* task_idx, float* mll, float* mll_sum, float* dtheta_lik, int32_t* info,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Forward pass of the learned mean / kernel-feature nets for every parameter vector at `npts` points
  * (LearnedGPRegressionModel.forward's NN calls, models.py:505-514; used by the eval-mode posterior,
  * GPR_meta_svgd.py:203-212).  x (npts, d) -> mean (P, npts) [mean_kind NN, else untouched / may be NULL],

@@ -298,6 +298,14 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
                                       const float* x, const float* y, const int32_t* task_idx, float* mll, float* mll_sum,
                                       float* dtheta_lik, int32_t* info, void* workspace, int64_t workspace_bytes,
                                       void* stream) {
+  return pacoh_meta_mll_fwd_bwd_ragged(arch, P, T, n, theta, x, y, nullptr, task_idx, mll, mll_sum, dtheta_lik, info, workspace,
+                                       workspace_bytes, stream);
+}
+
+extern "C" int pacoh_meta_mll_fwd_bwd_ragged(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n, const float* theta,
+                                             const float* x, const float* y, const int32_t* task_n, const int32_t* task_idx,
+                                             float* mll, float* mll_sum, float* dtheta_lik, int32_t* info, void* workspace,
+                                             int64_t workspace_bytes, void* stream) {
   Plan pl;
   int rc = make_plan(arch, P, T, n, &pl);
   if (rc != PACOH_OK) return rc;
@@ -347,7 +355,7 @@ extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32
 
   GpArgs ga;
   memset(&ga, 0, sizeof(ga));
-  ga.theta = theta; ga.x = x; ga.y = y; ga.task_idx = task_idx;
+  ga.theta = theta; ga.x = x; ga.y = y; ga.task_idx = task_idx; ga.task_n = task_n;
   ga.mean = pl.mean_nn ? ws + pl.off_mean : nullptr;
   ga.feat = pl.kern_nn ? ws + pl.off_feat : nullptr;
   ga.dmean = pl.mean_nn ? ws + pl.off_dmean : nullptr;

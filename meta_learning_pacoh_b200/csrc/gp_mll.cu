@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kerne
   const int pair = blockIdx.x * kGpWarps + warp;
   if (pair >= a.P * a.T) return;
   const int p = pair / a.T, t = pair - p * a.T;
-  const int n = a.n, F = a.F, Q = a.T * a.n;
+  const int ns = a.n, F = a.F, Q = a.T * a.n;               // ns: row stride of the (padded) task arrays
   const int src = __ldg(a.task_idx + t);
+  const int n = a.task_n != nullptr ? __ldg(a.task_n + src) : ns;   // ragged batches: this task's own number of points
   const float* th = a.theta + (size_t)p * a.D;
   float(*sf)[RS] = s_feat[warp];
 
@@ -209,15 +210,15 @@ __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kerne
   for (int s = 0; s < NS; ++s) {
     const int row = lane + 32 * s;
     valid[s] = row < n;
-    const size_t q = (size_t)p * Q + (size_t)t * n + row;
+    const size_t q = (size_t)p * Q + (size_t)t * ns + row;
     float m = cmean;
     if (a.mean != nullptr && valid[s]) m = __ldg(a.mean + q);
-    r[s] = valid[s] ? __ldg(a.y + (size_t)src * n + row) - m : 0.0f;
+    r[s] = valid[s] ? __ldg(a.y + (size_t)src * ns + row) - m : 0.0f;
 #pragma unroll
     for (int f = 0; f < FT; ++f) {
       float z = 0.0f;
       if (valid[s] && f < F)
-        z = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * n + row) * a.d + f);
+        z = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * ns + row) * a.d + f);
       u[s][f] = valid[s] ? z * inv_ls[f] : kFar;
     }
     if (row < NC) {
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kerne
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       const int row = lane + 32 * s;
-      if (row < n) {
-        const size_t q = (size_t)p * Q + (size_t)t * n + row;
+      if (row < ns) {
+        const size_t q = (size_t)p * Q + (size_t)t * ns + row;
         if (a.dmean != nullptr) a.dmean[q] = 0.0f;
         if (a.dfeat != nullptr)
           for (int f = 0; f < F; ++f) a.dfeat[q * F + f] = 0.0f;
@@ -407,8 +408,14 @@ __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kerne
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const int row = lane + 32 * s;
+    if (row >= n && row < ns) {   // padding rows of a ragged batch: the MLP backward must see exact zeros
+      const size_t q = (size_t)p * Q + (size_t)t * ns + row;
+      if (a.dmean != nullptr) a.dmean[q] = 0.0f;
+      if (a.dfeat != nullptr)
+        for (int f = 0; f < F; ++f) a.dfeat[q * F + f] = 0.0f;
+    }
     if (row < n) {
-      const size_t q = (size_t)p * Q + (size_t)t * n + row;
+      const size_t q = (size_t)p * Q + (size_t)t * ns + row;
       if (a.dmean != nullptr) a.dmean[q] = beta[s] * inv_n;
 #pragma unroll
       for (int f = 0; f < FT; ++f) {

@@ -102,8 +102,15 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
   const int p = blockIdx.y;                          // particle
   const bool pvalid = blockIdx.x * 2 + mtx < a.T;    // odd T: the last CTA's second matrix is a dummy
   const int t = pvalid ? blockIdx.x * 2 + mtx : a.T - 1;
-  const int n = a.n, F = a.F, Q = a.T * a.n;
+  const int ns = a.n, F = a.F, Q = a.T * a.n;               // ns: row stride of the (padded) task arrays
   const int src = __ldg(a.task_idx + t);
+  // ragged batches: every matrix has its own number of points n <= ns; the CTA-uniform loops run to the larger of the two
+  int n = ns, nloop = ns;
+  if (a.task_n != nullptr) {
+    const int t_other = min((int)blockIdx.x * 2 + (1 - mtx), a.T - 1);
+    n = __ldg(a.task_n + src);
+    nloop = max(n, __ldg(a.task_n + __ldg(a.task_idx + t_other)));
+  }
   const float* th = a.theta + (size_t)p * a.D;
   float(*sf)[RS] = s_feat[mtx];
 
@@ -140,16 +147,16 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
 
   // ---- this thread's row: residual and scaled features (padding rows sit "infinitely far" away => zero Gram rows)
   const bool valid = row < n;
-  const size_t q = (size_t)p * Q + (size_t)t * n + row;
+  const size_t q = (size_t)p * Q + (size_t)t * ns + row;
   float r = 0.0f, u[FT];
   {
     float m = a.mean_kind == PACOH_MEAN_CONSTANT ? __ldg(th + a.off_const_mean) : 0.0f;
     if (a.mean != nullptr && valid) m = __ldg(a.mean + q);
-    r = valid ? __ldg(a.y + (size_t)src * n + row) - m : 0.0f;
+    r = valid ? __ldg(a.y + (size_t)src * ns + row) - m : 0.0f;
 #pragma unroll
     for (int f = 0; f < FT; ++f) {
       u[f] = 0.0f;
-      if (valid && f < F) u[f] = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * n + row) * a.d + f);
+      if (valid && f < F) u[f] = a.feat != nullptr ? __ldg(a.feat + q * F + f) : __ldg(a.x + ((size_t)src * ns + row) * a.d + f);
     }
   }
   fence_before_sync();
@@ -165,9 +172,9 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t bar = smem_u32(&mbar);
   uint32_t parity = 0;
-  const int nblk = (n + 3) >> 2;       // 4-pivot blocks
-  const int ngrp = (n + 7) >> 3;       // 8-column groups of the row that are ever read
-  const uint32_t idesc = umma_idesc_tf32(128, ((n + 15) >> 4) << 4);
+  const int nblk = (nloop + 3) >> 2;   // 4-pivot blocks
+  const int ngrp = (nloop + 7) >> 3;   // 8-column groups of the row that are ever read
+  const uint32_t idesc = umma_idesc_tf32(128, ((nloop + 15) >> 4) << 4);
 
   float aug = 0.0f, tot = 0.0f, rho = 0.0f, logdet2 = 0.0f, dadd = 0.0f;
   int lvl = 0, status = -1;     // jitter level of this thread's matrix (uniform within the matrix)
@@ -340,6 +347,11 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
 
   if (pvalid) {
     float* hyp = a.dhyp + ((size_t)p * a.T + t) * gp_hyp_stride(F);
+    if (!valid && row < ns) {   // padding rows of a ragged batch: the MLP backward must see exact zeros
+      if (a.dmean != nullptr) a.dmean[q] = 0.0f;
+      if (a.dfeat != nullptr)
+        for (int f = 0; f < F; ++f) a.dfeat[q * F + f] = 0.0f;
+    }
     if (valid) {
       if (a.dmean != nullptr) a.dmean[q] = failed ? 0.0f : beta * inv_n;
       if (a.dfeat != nullptr) {

@@ -28,6 +28,7 @@ struct GpArgs {
   const float* x;         // raw inputs (covar SE uses them as features)
   const float* y;         // (T_total, n)
   const int* task_idx;    // (T)
+  const int* task_n;      // (T_total) points per task for ragged batches (rows n_t .. n-1 are padding), or nullptr
   const float* mean;      // (P, Q) or nullptr (zero / constant mean)
   const float* feat;      // (P, Q, F) or nullptr (SE on raw inputs)
   float* dmean;           // (P, Q) or nullptr

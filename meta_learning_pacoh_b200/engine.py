@@ -148,8 +148,10 @@ def _f32c(t, device):
 class MetaMLLEngine:
     """Device-resident task set + workspaces for the batched marginal log-likelihood (pacoh_meta_mll_fwd_bwd)."""
 
-    def __init__(self, arch: GPArch, x, y, device=None):
-        """x (T_total, n, d), y (T_total, n): normalised task data (abstract.py:224-258), uploaded once."""
+    def __init__(self, arch: GPArch, x, y, device=None, task_n=None):
+        """x (T_total, n, d), y (T_total, n): normalised task data (abstract.py:224-258), uploaded once.
+        ``task_n`` (T_total,) ints: ragged task sets -- x / y are padded to n = max_t n_t rows and task t only uses its
+        first task_n[t] rows (pacoh_meta_mll_fwd_bwd_ragged); None: every task has n points."""
         self.arch = arch
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
@@ -160,6 +162,12 @@ class MetaMLLEngine:
         self.x = x.contiguous().to(self.device)
         self.y = y.contiguous().to(self.device)
         self.T_total, self.n, self.d = x.shape
+        self.task_n = None
+        if task_n is not None:
+            tn = torch.as_tensor(task_n, dtype=torch.int32).reshape(-1)
+            assert tn.numel() == self.T_total and int(tn.min()) >= 1 and int(tn.max()) <= self.n
+            if int(tn.min()) < self.n:
+                self.task_n = tn.contiguous().to(self.device)
         self._c_arch = arch.c_struct()
         self._ws = {}
 
@@ -188,9 +196,9 @@ class MetaMLLEngine:
         info = torch.empty(P, T, dtype=torch.int32, device=self.device) if want_info else None
         dth_ptr = ctypes.c_void_p(packed.data_ptr())
         sum_ptr = ctypes.c_void_p(packed.data_ptr() + 4 * P * D)
-        check(lib.pacoh_meta_mll_fwd_bwd(ctypes.byref(self._c_arch), P, T, self.n, _ptr(theta), _ptr(self.x), _ptr(self.y),
-                                         _ptr(task_idx), _ptr(mll), sum_ptr, dth_ptr, _ptr(info), _ptr(ws), ws.numel(),
-                                         _stream()))
+        check(lib.pacoh_meta_mll_fwd_bwd_ragged(ctypes.byref(self._c_arch), P, T, self.n, _ptr(theta), _ptr(self.x), _ptr(self.y),
+                                                _ptr(self.task_n), _ptr(task_idx), _ptr(mll), sum_ptr, dth_ptr, _ptr(info),
+                                                _ptr(ws), ws.numel(), _stream()))
         return mll, packed, info
 
 

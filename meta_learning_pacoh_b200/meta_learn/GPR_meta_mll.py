@@ -64,7 +64,7 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         self.shared_parameters.append({'params': [self.raw_noise], 'lr': self.lr_params})
 
         X, Y = self._build_task_dicts(meta_train_data)
-        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
+        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
         self._setup_optimizer(optimizer, lr_params, lr_decay)
         self.fitted = False
 

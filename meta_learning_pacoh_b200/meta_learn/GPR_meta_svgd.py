@@ -50,7 +50,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
                                     kernel, bandwidth, optimizer, lr, lr_decay)
 
         X, Y = self._build_task_dicts(meta_train_data)
-        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
+        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
         self._idx_host = torch.empty(self.task_batch_size, dtype=torch.int32).pin_memory()
         self._group, self._peer = None, None
         self._rank, self._world = 0, 1
@@ -113,7 +113,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             self._idx_host = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
         self._idx_host[:hi - lo].copy_(torch.from_numpy(idx[lo:hi]))
         idx_dev = self._idx_host[:hi - lo].to(self.device, non_blocking=True)
-        pre = eng.pre_factor([self.engine.n] * T)                      # GLOBAL batch (random_gp.py:209-212)
+        pre = eng.pre_factor(self.task_sizes[idx])                     # GLOBAL batch, harmonic mean of its n_t (random_gp.py:209-212)
         self._phi.prepare(self.particles)                              # K(theta) on a side stream, under the MLL kernels
         logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
                                                         self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
@@ -138,6 +138,8 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         passed and sliced here.  ``wait=False`` returns ``(logp_pinned, event)`` without synchronising: the device->host
         copy of logp is in flight and ``event.synchronize()`` must precede any read -- lets the caller prepare the next
         batch on the host while this step runs (the copies and the read-back still happen every step)."""
+        if self._ragged:
+            raise NotImplementedError("svgd_step_host takes dense (T, n, d) host batches: use svgd_step for ragged task sets")
         if global_tasks is None:
             T = x_batch.shape[0]
             lo, hi = eng.shard_bounds(T, self._rank, self._world)

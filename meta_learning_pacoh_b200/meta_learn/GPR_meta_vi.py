@@ -92,7 +92,7 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
         self._setup_optimizer(optimizer, lr, lr_decay)
 
         X, Y = self._build_task_dicts(meta_train_data)
-        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device)
+        self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
         self._group, self._rank, self._world = None, 0, 1
         self._last_info = None
         self.fitted = False
@@ -136,7 +136,7 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
         idx = np.asarray(task_idx, dtype=np.int32)
         T = idx.shape[0]
         lo, hi = eng.shard_bounds(T, self._rank, self._world)
-        return torch.from_numpy(idx[lo:hi].copy()).to(self.device), eng.pre_factor([self.engine.n] * T)
+        return torch.from_numpy(idx[lo:hi].copy()).to(self.device), eng.pre_factor(self.task_sizes[idx])
 
     def get_neg_elbo(self, task_idx, eps=None):
         """-mean_s [ log p(theta_s | data) - prior_factor * log q(theta_s) ] and its gradient w.r.t. the posterior

@@ -127,18 +127,27 @@ class RegressionModelMetaLearned:
 
     def _build_task_dicts(self, meta_train_data):
         """Per-task tensors (task_dict['train_x'], ['train_y'] as in the reference) plus the stacked, device-resident
-        (T, n, d) / (T, n) arrays the kernels index with the sampled task ids."""
+        (T, n, d) / (T, n) arrays the kernels index with the sampled task ids.  Tasks may have different numbers of
+        points (the reference loops over tasks, random_gp.py:214-217): the arrays are zero-padded to the largest task
+        and ``self.task_sizes`` holds every task's own n_t for the kernels (ragged entry point) and for the
+        harmonic-mean pre-factor (random_gp.py:209-212)."""
         self.task_dicts = []
         for train_x, train_y in meta_train_data:
             x_t, y_t = self._prepare_data_per_task(train_x, train_y)
             self.task_dicts.append({"train_x": x_t, "train_y": y_t})
-        sizes = {td["train_x"].shape[0] for td in self.task_dicts}
-        if len(sizes) != 1:
-            raise NotImplementedError("tasks with different numbers of points are not supported by the CUDA path yet "
-                                      "(SURVEY 8(f).3: ragged task batches)")
-        X = torch.stack([td["train_x"] for td in self.task_dicts])
-        Y = torch.stack([td["train_y"] for td in self.task_dicts])
+        self.task_sizes = np.asarray([td["train_x"].shape[0] for td in self.task_dicts], dtype=np.int64)
+        n_max = int(self.task_sizes.max())
+        d = self.task_dicts[0]["train_x"].shape[1]
+        X = torch.zeros(len(self.task_dicts), n_max, d, dtype=torch.float32)
+        Y = torch.zeros(len(self.task_dicts), n_max, dtype=torch.float32)
+        for t, td in enumerate(self.task_dicts):
+            X[t, :self.task_sizes[t]] = td["train_x"].cpu()
+            Y[t, :self.task_sizes[t]] = td["train_y"].cpu()
         return X, Y
+
+    @property
+    def _ragged(self):
+        return bool(self.task_sizes.min() != self.task_sizes.max())
 
     def _sample_task_indices(self):
         """rds_numpy.choice(self.task_dicts, size=B) of the reference (GPR_meta_svgd.py:102) draws the same index

@@ -104,6 +104,37 @@ def test_svgd_imq_kernel_learner_steps(ml):
     assert torch.isfinite(m.particles).all()
 
 
+def test_learners_accept_ragged_task_sets(ml):
+    """meta_train_data with different numbers of points per task (what the reference's per-task loop takes, e.g. the
+    real-world datasets of its experiments): all three learners train and predict; the SVGD logp of the first step equals
+    the oracle's on the same normalised tasks (harmonic-mean pre-factor included)."""
+    rs = np.random.RandomState(2)
+    tasks = []
+    for t in range(10):
+        n_t = int(rs.randint(4, 41))
+        x = rs.uniform(-5, 5, size=(n_t, 1))
+        tasks.append((x, np.sin(x) * rs.uniform(0.7, 1.3) + 0.1 * rs.normal(size=(n_t, 1))))
+    m = ml.GPRegressionMetaLearnedSVGD(tasks, num_particles=4, random_seed=5, num_iter_fit=3)
+    assert m._ragged and m.engine.task_n is not None
+    idx = m._sample_task_indices()
+    theta0 = m.particles.detach().clone()
+    logp = m.svgd_step(idx)
+    norm_tasks = [(td["train_x"].cpu().double(), td["train_y"].cpu().double()) for td in m.task_dicts]
+    lay = orc.Layout(1)
+    mu64, s64 = orc.hyper_prior_params(lay, m.weight_prior_std, m.bias_prior_std, torch.float64)
+    logp64 = orc.meta_log_prob(theta0.cpu().double(), lay, [norm_tasks[i] for i in idx], m.prior_factor, mu64, s64)
+    assert (logp.cpu().double() - logp64).abs().max().item() <= 1e-4 * logp64.abs().max().item()
+    m.meta_fit(verbose=False)
+    x_c, y_c = tasks[0]
+    mean, std = m.predict(x_c, y_c, np.linspace(-5, 5, 30))
+    assert np.isfinite(mean).all() and np.isfinite(std).all()
+    for cls, kw in ((ml.GPRegressionMetaLearnedVI, dict(svi_batch_size=4)), (ml.GPRegressionMetaLearned, dict(task_batch_size=4))):
+        m2 = cls(tasks, random_seed=6, num_iter_fit=3, **kw)
+        m2.meta_fit(verbose=False)
+        mean, std = m2.predict(x_c, y_c, np.linspace(-5, 5, 30))
+        assert np.isfinite(mean).all() and np.isfinite(std).all()
+
+
 def test_svgd_seed_determinism(ml):
     """tests/test_GPR.py:173-187 style: two runs with the same seed are bit-identical."""
     train, test = orc.sinusoid_tasks(12, 8, seed=3, n_test=20)

@@ -217,6 +217,42 @@ def test_tensor_core_gp_kernel_shapes(eng, n, kw):
         assert_groups(arch, score, g64)
 
 
+@pytest.mark.parametrize("n_max,lo,kw", [
+    (20, 3, dict(input_dim=1)),                                                            # register GP kernel
+    (50, 33, dict(input_dim=1)),                                                           # tensor-memory GP kernel, all sizes > 32
+    (64, 1, dict(input_dim=2, mean_kind="zero", covar_kind="NN")),                          # both kernels' size range in one batch
+    (40, 7, dict(input_dim=3, mean_kind="constant", covar_kind="SE")),
+    (57, 20, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),                        # PACOH-MAP variant
+])
+def test_ragged_task_sets_match_oracle(eng, n_max, lo, kw):
+    """Tasks with different numbers of points (the reference's per-task loop handles them implicitly, random_gp.py:214-217;
+    pre-factor with the harmonic mean, :209-212): padded arrays + task_n through pacoh_meta_mll_fwd_bwd_ragged."""
+    T_total, d = 9, kw["input_dim"]
+    rs = np.random.RandomState(n_max + lo)
+    sizes = rs.randint(lo, n_max + 1, size=T_total)
+    sizes[0], sizes[1] = n_max, lo
+    x = rs.uniform(-2, 2, size=(T_total, n_max, d)).astype(np.float32)
+    y = (np.sin(2 * x[..., 0]) + 0.1 * rs.normal(size=(T_total, n_max))).astype(np.float32)
+    for t in range(T_total):                                  # poison the padding: it must not influence anything
+        x[t, sizes[t]:] = 7.5
+        y[t, sizes[t]:] = -3.0
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    theta = _prior_particles(lay, 3, 5 + n_max)
+    idx = [8, 1, 1, 0, 2, 3, 4, 7, 6, 5, 0]
+    e = eng.MetaMLLEngine(arch, x, y, DEV, task_n=sizes)
+    th = torch.from_numpy(theta).to(DEV)
+    mll, packed, info = e.mll_fwd_bwd(th, torch.tensor(idx, dtype=torch.int32, device=DEV))
+    mu, sigma = arch.hyper_prior(0.5, 3.0)
+    pre = eng.pre_factor(sizes[idx])
+    logp, dth = eng.logprob_finalize(th, mu.to(DEV), sigma.to(DEV), 0.01, pre, packed)
+    tasks = [(torch.from_numpy(x[t, :sizes[t]]).double(), torch.from_numpy(y[t, :sizes[t]]).double()) for t in range(T_total)]
+    mu64, s64 = orc.hyper_prior_params(lay, 0.5, 3.0, torch.float64)
+    logp64, g64, mll64 = orc.meta_log_prob_and_grad(torch.from_numpy(theta).double(), lay, [tasks[i] for i in idx], 0.01, mu64, s64)
+    assert (info.cpu().numpy() == 0).all()
+    assert relmax(mll.cpu().numpy(), mll64.numpy()) <= RTOL and relmax(logp.cpu().numpy(), logp64.numpy()) <= RTOL
+    assert_groups(arch, dth.cpu().numpy(), g64.numpy())
+
+
 def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
     """BASELINE config #1: the engine's P=1 ScaleRBF/noise-floor path reproduces demo.ipynb's 'Loss: 5.755850'."""
     train = orc.sinusoid_tasks(20, 5, seed=26)

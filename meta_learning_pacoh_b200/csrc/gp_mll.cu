@@ -492,7 +492,8 @@ int launch_gp_mll(const GpArgs& a, cudaStream_t st) {
     const char* e = getenv("PACOH_GP");
     tc = (e != nullptr && strcmp(e, "warp") == 0) ? 0 : 1;
   }
-  if (tc == 1 && a.n > 32 && a.F <= 4) return launch_gp_mll_tc(a, st);
+  if ((tc == 1 || a.n > 64) && a.n > 32 && a.F <= 4) return launch_gp_mll_tc(a, st);
+  if (a.n > 64) return PACOH_ERR_UNSUPPORTED;          // the register kernel holds at most 64 columns per lane pair
   if (a.F <= 2) return dispatch_nc4_f2(a, st);
   if (a.F <= 4) return dispatch_nc16<4>(a, st);
   return dispatch_nc16<16>(a, st);

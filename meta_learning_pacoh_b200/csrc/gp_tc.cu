@@ -1,9 +1,10 @@
-// Batched GP marginal log-likelihood with analytic gradient -- tensor-memory / tcgen05 version for 32 < n <= 64, sm_100a.
+// Batched GP marginal log-likelihood with analytic gradient -- tensor-memory / tcgen05 version for 32 < n <= 128, sm_100a.
 //
 // Same mathematics and outputs as gp_mll_kernel (gp_mll.cu; reference: meta_learn/random_gp.py:54-89, models.py:428-487,
 // gpytorch ExactMarginalLogLikelihood at random_gp.py:83-85 and its autograd reverse pass, svgd.py:16), different mapping:
 //
-//   CTA = 128 threads = TWO (particle, task) matrices; thread (m = tid >> 6, row = tid & 63) owns one matrix row.
+//   CTA = 128 threads = TWO (particle, task) matrices for n <= 64 (ONE for 64 < n <= 128: same code, MT = 1);
+//   thread (m = tid >> 6, row = tid & 63) owns one matrix row.
 //   The normalised matrix lives in TENSOR MEMORY: row r of matrix m is TMEM lane 64 m + r, columns 0..63 (fp32).
 //   Blocked symmetric Gauss-Jordan, 4 pivots per block.  Per block
 //     1. every thread reads its 4 block-column entries with tcgen05.ld at a RUNTIME column offset (tensor memory is
@@ -28,9 +29,7 @@ namespace {
 using namespace tc;
 
 constexpr int kGT = 128;           // threads per CTA
-constexpr int kRows = 64;          // rows per matrix
 constexpr float kFar = 1.0e18f;    // scaled feature of a padding row: exp2(-(1e18)^2) == 0 exactly
-constexpr int kGpTmemCols = 64;
 #ifndef PACOH_GPTC_MINB
 #define PACOH_GPTC_MINB 8   // CTAs per SM the register allocation is capped for (tensor memory allows 8)
 #endif
@@ -59,6 +58,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
 }
 
+// hi part of the 3xTF32 split.  Two matrices per CTA (n <= 64): truncation (one LOP).  One matrix per CTA (n <= 128): the
+// sweep runs over twice as many pivots and the accumulated rounding error of truncated splits (biased, lo up to 2^-11)
+// was measured at 1.3e-4 on the kernel-net gradients for n = 97; round-to-nearest (lo <= 2^-12, unbiased) costs one IADD.
+template <int MT>
+__device__ __forceinline__ float split_hi(float v) {
+  return tf32_hi(v);
+}
+
 // In-register symmetric sweep of the 4x4 pivot block: B <- -B^-1 (only the upper triangle B[i][j], i <= j, is read or
 // written; the swept matrix stays symmetric); its pivots are the Schur diagonals d_k = L_kk^2.
 #define PACOH_SYM(i, j) B[(i) < (j) ? (i) : (j)][(i) < (j) ? (j) : (i)]
@@ -84,41 +91,54 @@ __device__ __forceinline__ void invert4_sym(float (&B)[4][4], bool& ok, float& l
   }
 }
 
-template <int FT>
-__global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
+// MT = matrices per CTA: 2 (n <= 64: 64 rows / TMEM columns each, 8 CTAs per SM) or 1 (64 < n <= 128: 128 rows and
+// columns, 4 CTAs per SM; the K-slots 4-7 of both MMA operands are a constant zero plane).
+template <int FT, int MT>
+__global__ void __launch_bounds__(kGT, (MT == 2 ? PACOH_GPTC_MINB : 4)) gp_tc_kernel(GpArgs a) {
   constexpr int RS = ((FT + 1 + 3) / 4) * 4;   // smem feature row: FT scaled features, then alpha
-  __shared__ __align__(1024) float s_x_hi[kRows * 8], s_x_lo[kRows * 8];     // UMMA B operand X [64 x 8], K-major
+  constexpr int kRows = kGT / MT;              // rows (= TMEM columns) per matrix
+  constexpr int WPM = 4 / MT;                  // warps per matrix
+  constexpr int kCols = kRows;                 // tensor-memory columns of the CTA
+  __shared__ __align__(1024) float s_x_hi[kRows * 8], s_x_lo[kRows * 8];     // UMMA B operand X [kRows x 8], K-major
   __shared__ __align__(1024) float s_w_hi[kGT * 8], s_w_lo[kGT * 8];         // UMMA A operand W [128 x 8], K-major
-  __shared__ __align__(16) float s_t0[2][kRows][4];                          // published block columns (true values)
-  __shared__ __align__(16) float s_aug[2][4];
-  __shared__ __align__(16) float s_feat[2][kRows][RS];
-  __shared__ float s_red[2][2][8];                                           // [matrix][warp-in-matrix][slot]
-  __shared__ float s_hyp[2][8][2];                                           // hyper-parameters, one per designated thread
+  __shared__ __align__(16) float s_t0[MT][kRows][4];                          // published block columns (true values)
+  __shared__ __align__(16) float s_aug[MT][4];
+  __shared__ __align__(16) float s_feat[MT][kRows][RS];
+  __shared__ float s_red[MT][WPM][8];                                        // [matrix][warp-in-matrix][slot]
+  __shared__ float s_hyp[MT][8][2];                                           // hyper-parameters, one per designated thread
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mtx = tid >> 6, row = tid & 63, wim = warp & 1;
+  const int mtx = tid / kRows, row = tid % kRows, wim = warp % WPM;
+  const int kplane = MT == 2 ? mtx : 0;              // K-slot plane (4 slots) this matrix owns in the MMA operands
   const int p = blockIdx.y;                          // particle
-  const bool pvalid = blockIdx.x * 2 + mtx < a.T;    // odd T: the last CTA's second matrix is a dummy
-  const int t = pvalid ? blockIdx.x * 2 + mtx : a.T - 1;
+  const bool pvalid = blockIdx.x * MT + mtx < a.T;   // odd T: the last CTA's second matrix is a dummy
+  const int t = pvalid ? blockIdx.x * MT + mtx : a.T - 1;
   const int ns = a.n, F = a.F, Q = a.T * a.n;               // ns: row stride of the (padded) task arrays
   const int src = __ldg(a.task_idx + t);
   // ragged batches: every matrix has its own number of points n <= ns; the CTA-uniform loops run to the larger of the two
   int n = ns, nloop = ns;
   if (a.task_n != nullptr) {
-    const int t_other = min((int)blockIdx.x * 2 + (1 - mtx), a.T - 1);
     n = __ldg(a.task_n + src);
-    nloop = max(n, __ldg(a.task_n + __ldg(a.task_idx + t_other)));
+    nloop = n;
+    if (MT == 2) {
+      const int t_other = min((int)blockIdx.x * 2 + (1 - mtx), a.T - 1);
+      nloop = max(n, __ldg(a.task_n + __ldg(a.task_idx + t_other)));
+    }
   }
   const float* th = a.theta + (size_t)p * a.D;
   float(*sf)[RS] = s_feat[mtx];
 
-  if (warp == 0) tmem_alloc<kGpTmemCols>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<kCols>(&tmem_base_s);
   if (tid == 0) mbar_init(smem_u32(&mbar), 1);
   // the K-slots of the OTHER matrix are zero in this row of W, for the whole kernel
-  sts4(s_w_hi + ((tid + (1 - mtx) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
-  sts4(s_w_lo + ((tid + (1 - mtx) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+  sts4(s_w_hi + ((tid + (1 - kplane) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+  sts4(s_w_lo + ((tid + (1 - kplane) * kGT) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+  if (MT == 1) {   // one matrix: the second K plane of X is zero as well
+    sts4(s_x_hi + ((row + kRows) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+    sts4(s_x_lo + ((row + kRows) << 2), make_float4(0.f, 0.f, 0.f, 0.f));
+  }
 
   // ---- hyper-parameters (random_gp.py:69-73; MAP: GPR_meta_mll.py:54-55,218)
   //      computed once per matrix: rows 0..FT-1 take a lengthscale each, row 4 the noise, row 5 the output scale;
@@ -231,9 +251,9 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
         *reinterpret_cast<float4*>(&s_t0[mtx][row][0]) = make_float4(t0[0], t0[1], t0[2], t0[3]);
         float hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { hi[j] = tf32_hi(xv[j]); lo[j] = xv[j] - hi[j]; }
-        sts4(s_x_hi + ((row + mtx * kRows) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts4(s_x_lo + ((row + mtx * kRows) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
+        for (int j = 0; j < 4; ++j) { hi[j] = split_hi<MT>(xv[j]); lo[j] = xv[j] - hi[j]; }
+        sts4(s_x_hi + ((row + kplane * kRows) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts4(s_x_lo + ((row + kplane * kRows) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
         if (inb) s_aug[mtx][rel] = aug;
       }
       __syncthreads();
@@ -262,9 +282,9 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
       {
         float hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { hi[j] = tf32_hi(nw[j]); lo[j] = nw[j] - hi[j]; }
-        sts4(s_w_hi + ((tid + mtx * kGT) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts4(s_w_lo + ((tid + mtx * kGT) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
+        for (int j = 0; j < 4; ++j) { hi[j] = split_hi<MT>(nw[j]); lo[j] = nw[j] - hi[j]; }
+        sts4(s_w_hi + ((tid + kplane * kGT) << 2), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts4(s_w_lo + ((tid + kplane * kGT) << 2), make_float4(lo[0], lo[1], lo[2], lo[3]));
       }
       fence_async_smem();
       fence_before_sync();
@@ -367,15 +387,22 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
         *mll_out = CUDART_NAN_F;
         for (int f = 0; f < F + 3; ++f) hyp[f] = 0.0f;
       } else {
-        const float quad = (s_red[mtx][0][0] + s_red[mtx][1][0]) * inv_tot;
-        const float Skt = (s_red[mtx][0][1] + s_red[mtx][1][1]) - (float)n * (1.0f + rho);
-        const float Str = s_red[mtx][0][2] + s_red[mtx][1][2];
-        const float dms = (s_red[mtx][0][3] + s_red[mtx][1][3]) * inv_n;
+        float tot_red[4 + FT];
+#pragma unroll
+        for (int i = 0; i < 4 + FT; ++i) {
+          tot_red[i] = 0.0f;
+#pragma unroll
+          for (int w = 0; w < WPM; ++w) tot_red[i] += s_red[mtx][w][i];
+        }
+        const float quad = tot_red[0] * inv_tot;
+        const float Skt = tot_red[1] - (float)n * (1.0f + rho);
+        const float Str = tot_red[2];
+        const float dms = tot_red[3] * inv_n;
         const float logdet = (float)n * logf(tot) + logdet2 * 0.69314718055994530942f;
         *mll_out = (-0.5f * quad - 0.5f * logdet - 0.5f * (float)n * 1.83787706640934548356f) * inv_n;
 #pragma unroll
         for (int f = 0; f < FT; ++f)
-          if (f < F) hyp[f] = rho * inv_n * (s_red[mtx][0][4 + f] + s_red[mtx][1][4 + f]) * s_hyp[mtx][f][1];
+          if (f < F) hyp[f] = rho * inv_n * tot_red[4 + f] * s_hyp[mtx][f][1];
         hyp[F] = 0.5f * inv_tot * inv_n * Str * s_hyp[mtx][4][1];
         hyp[F + 1] = 0.5f * inv_tot * inv_n * Skt * s_hyp[mtx][5][1];
         hyp[F + 2] = dms;
@@ -384,24 +411,32 @@ __global__ void __launch_bounds__(kGT, PACOH_GPTC_MINB) gp_tc_kernel(GpArgs a) {
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<kGpTmemCols>(tmem);
+  if (warp == 0) tmem_dealloc<kCols>(tmem);
 }
 
 }  // namespace
 
-// Tensor-core GP kernel: 32 < n <= 64 and F <= 4 (FT + 4 reduction slots <= 8).
+// Tensor-memory GP kernel: 32 < n <= 64 (two matrices per CTA) and 64 < n <= 128 (one), F <= 4 (FT + 4 reduction slots <= 8).
 int launch_gp_mll_tc(const GpArgs& a, cudaStream_t st) {
-  if (a.n <= 32 || a.n > 64 || a.F < 1 || a.F > 4) return PACOH_ERR_UNSUPPORTED;
+  if (a.n <= 32 || a.n > 128 || a.F < 1 || a.F > 4) return PACOH_ERR_UNSUPPORTED;
   if (a.P > 65535) return PACOH_ERR_UNSUPPORTED;
   static bool carveout_set = false;
   if (!carveout_set) {   // 8 CTAs / SM need 8 x 17 KB of shared memory: ask for the large carve-out (L1 is not used)
-    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     carveout_set = true;
   }
-  const dim3 grid((a.T + 1) / 2, a.P);
-  if (a.F <= 2) gp_tc_kernel<2><<<grid, kGT, 0, st>>>(a);
-  else gp_tc_kernel<4><<<grid, kGT, 0, st>>>(a);
+  if (a.n <= 64) {
+    const dim3 grid((a.T + 1) / 2, a.P);
+    if (a.F <= 2) gp_tc_kernel<2, 2><<<grid, kGT, 0, st>>>(a);
+    else gp_tc_kernel<4, 2><<<grid, kGT, 0, st>>>(a);
+  } else {
+    const dim3 grid(a.T, a.P);
+    if (a.F <= 2) gp_tc_kernel<2, 1><<<grid, kGT, 0, st>>>(a);
+    else gp_tc_kernel<4, 1><<<grid, kGT, 0, st>>>(a);
+  }
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

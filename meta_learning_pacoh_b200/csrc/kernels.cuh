@@ -41,7 +41,7 @@ struct GpArgs {
   float noise_floor;
   int off_ls, off_noise, off_oscale, off_const_mean;
 };
-constexpr int kMaxGpN = 64;    // warp-per-matrix kernel: n <= 64
+constexpr int kMaxGpN = 128;   // register kernel: n <= 64; tensor-memory kernel: 32 < n <= 128 (feature dim <= 4)
 constexpr int kMaxGpF = 16;    // feature dim
 __host__ __device__ inline int gp_hyp_stride(int F) { return F + 3; }
 int launch_gp_mll(const GpArgs& a, cudaStream_t st);

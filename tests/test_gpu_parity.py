@@ -60,6 +60,14 @@ def oracle64(lay, x, y, theta, idx, prior_factor=0.01, wstd=0.5, bstd=3.0):
     return mll.numpy(), logp.numpy(), g.numpy()
 
 
+# Extended range 64 < n <= 128 (no BASELINE config lives there): the in-place Gauss-Jordan sweep over twice as many pivots
+# is measurably less accurate than a Cholesky solve on ill-conditioned Gram matrices -- worst per-group gradient error
+# against fp64 over random prior particles (tests/manual/gp_accuracy_vs_n.py): 2e-5 .. 7e-5 for n = 65 .. 112 and 4e-4
+# for one n = 128 case, where the fp32 oracle (the reference's own precision) sits at 1e-5 .. 5e-5.  Values (mll, logp)
+# hold the 1e-4 bar everywhere; gradients for n > 64 are tested at 5e-4.
+RTOL_N128 = 5e-4
+
+
 def assert_groups(arch, got, want, tol=RTOL):
     """per parameter group, error in the group's max-norm; groups whose true gradient is (numerically) zero -- the kernel
     net's output bias, to which the stationary SE kernel is invariant, only sees the tiny prior term -- are measured
@@ -156,9 +164,11 @@ def _prior_particles(lay, P, seed):
     return (mu + sigma * torch.randn(P, lay.D, generator=g)).numpy()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 20, 31, 32, 33, 40, 47, 48, 49, 50, 52, 63, 64])
-def test_every_matrix_size_up_to_64(eng, n):
-    """all NC instantiations of the warp-per-matrix kernel, ragged last tile of the MLP kernels, repeated tasks."""
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 20, 31, 32, 33, 40, 47, 48, 49, 50, 52, 63, 64,
+                               65, 72, 80, 97, 100, 112, 127, 128])
+def test_every_matrix_size_up_to_128(eng, n):
+    """all NC instantiations of the warp-per-matrix kernel (n <= 32), the tensor-memory kernel with two matrices per CTA
+    (n <= 64) and with one (n <= 128), ragged last tile of the MLP kernels, repeated tasks."""
     x, y = _synthetic(5, n, seed=n)
     lay, arch = orc.Layout(1), eng.GPArch(1)
     theta = _prior_particles(lay, 3, 100 + n)
@@ -167,7 +177,7 @@ def test_every_matrix_size_up_to_64(eng, n):
     mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
     assert (info == 0).all()
     assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
-    assert_groups(arch, score, g64)
+    assert_groups(arch, score, g64, tol=RTOL if n <= 64 else RTOL_N128)
 
 
 @pytest.mark.parametrize("kw", [
@@ -203,6 +213,8 @@ def test_architectures_match_oracle(eng, kw):
     (41, dict(input_dim=2, mean_kind="zero", covar_kind="NN")),
     (57, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),                              # PACOH-MAP variant
     (50, dict(input_dim=1, mean_kind="constant", covar_kind="SE")),
+    (90, dict(input_dim=3, mean_layers=(32, 32), kernel_layers=(32, 32), feature_dim=4)),    # one matrix per CTA, FT = 4
+    (128, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),
 ])
 def test_tensor_core_gp_kernel_shapes(eng, n, kw):
     """gp_tc.cu (32 < n <= 64): feature widths, mean kinds, output scale, odd task counts (the dummy second matrix)."""
@@ -214,7 +226,7 @@ def test_tensor_core_gp_kernel_shapes(eng, n, kw):
         mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
         assert (info == 0).all()
         assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
-        assert_groups(arch, score, g64)
+        assert_groups(arch, score, g64, tol=RTOL if n <= 64 else RTOL_N128)
 
 
 @pytest.mark.parametrize("n_max,lo,kw", [
@@ -223,6 +235,7 @@ def test_tensor_core_gp_kernel_shapes(eng, n, kw):
     (64, 1, dict(input_dim=2, mean_kind="zero", covar_kind="NN")),                          # both kernels' size range in one batch
     (40, 7, dict(input_dim=3, mean_kind="constant", covar_kind="SE")),
     (57, 20, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),                        # PACOH-MAP variant
+    (100, 40, dict(input_dim=1)),                                                          # one matrix per CTA
 ])
 def test_ragged_task_sets_match_oracle(eng, n_max, lo, kw):
     """Tasks with different numbers of points (the reference's per-task loop handles them implicitly, random_gp.py:214-217;
@@ -250,7 +263,7 @@ def test_ragged_task_sets_match_oracle(eng, n_max, lo, kw):
     logp64, g64, mll64 = orc.meta_log_prob_and_grad(torch.from_numpy(theta).double(), lay, [tasks[i] for i in idx], 0.01, mu64, s64)
     assert (info.cpu().numpy() == 0).all()
     assert relmax(mll.cpu().numpy(), mll64.numpy()) <= RTOL and relmax(logp.cpu().numpy(), logp64.numpy()) <= RTOL
-    assert_groups(arch, dth.cpu().numpy(), g64.numpy())
+    assert_groups(arch, dth.cpu().numpy(), g64.numpy(), tol=RTOL if n_max <= 64 else RTOL_N128)
 
 
 def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
@@ -285,7 +298,7 @@ def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
     assert_groups(arch, got, g_ref.numpy().reshape(1, -1), tol=2e-4)
 
 
-@pytest.mark.parametrize("n", [8, 40])      # register kernel / tensor-memory kernel (two matrices per CTA retry together)
+@pytest.mark.parametrize("n", [8, 40, 96])  # register kernel / tensor-memory kernel (two matrices per CTA retry together) / one per CTA
 def test_jitter_ladder_and_not_psd_reporting(eng, n):
     """duplicate inputs + vanishing noise: singular K.  The kernel must climb the 1e-6/1e-5/1e-4 jitter ladder
     (gpytorch psd_safe_cholesky) or report failure; the host wrapper raises NotPSDError on failure."""
@@ -316,7 +329,7 @@ def test_jitter_ladder_and_not_psd_reporting(eng, n):
 def test_unsupported_sizes_fail_loudly(eng):
     from meta_learning_pacoh_b200._lib import PacohError
     arch = eng.GPArch(1)
-    x, y = _synthetic(2, 80)
+    x, y = _synthetic(2, 130)
     e = eng.MetaMLLEngine(arch, x, y, DEV)
     with pytest.raises(PacohError):
         e.mll_fwd_bwd(torch.zeros(2, arch.D, device=DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))

@@ -58,9 +58,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
 }
 
-// hi part of the 3xTF32 split.  Two matrices per CTA (n <= 64): truncation (one LOP).  One matrix per CTA (n <= 128): the
-// sweep runs over twice as many pivots and the accumulated rounding error of truncated splits (biased, lo up to 2^-11)
-// was measured at 1.3e-4 on the kernel-net gradients for n = 97; round-to-nearest (lo <= 2^-12, unbiased) costs one IADD.
+// hi part of the 3xTF32 split: truncation (one LOP; the tensor core would truncate anyway).  Round-to-nearest splitting
+// was tried for the one-matrix-per-CTA variant (n <= 128) and did not improve its accuracy (the error there comes from the
+// in-place Gauss-Jordan sweep itself), so both variants share this.
 template <int MT>
 __device__ __forceinline__ float split_hi(float v) {
   return tf32_hi(v);

@@ -93,7 +93,8 @@ __device__ __forceinline__ void invert4_sym(float (&B)[4][4], bool& ok, float& l
 
 // MT = matrices per CTA: 2 (n <= 64: 64 rows / TMEM columns each, 8 CTAs per SM) or 1 (64 < n <= 128: 128 rows and
 // columns, 4 CTAs per SM; the K-slots 4-7 of both MMA operands are a constant zero plane).
-template <int FT, int MT>
+// RAG: ragged batches (per-task n from a.task_n); the dense instantiation keeps n a launch constant.
+template <int FT, int MT, bool RAG>
 __global__ void __launch_bounds__(kGT, (MT == 2 ? PACOH_GPTC_MINB : 4)) gp_tc_kernel(GpArgs a) {
   constexpr int RS = ((FT + 1 + 3) / 4) * 4;   // smem feature row: FT scaled features, then alpha
   constexpr int kRows = kGT / MT;              // rows (= TMEM columns) per matrix
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kGT, (MT == 2 ? PACOH_GPTC_MINB : 4)) gp_tc_ke
   const int src = __ldg(a.task_idx + t);
   // ragged batches: every matrix has its own number of points n <= ns; the CTA-uniform loops run to the larger of the two
   int n = ns, nloop = ns;
-  if (a.task_n != nullptr) {
+  if (RAG) {
     n = __ldg(a.task_n + src);
     nloop = n;
     if (MT == 2) {
@@ -420,23 +421,27 @@ __global__ void __launch_bounds__(kGT, (MT == 2 ? PACOH_GPTC_MINB : 4)) gp_tc_ke
 int launch_gp_mll_tc(const GpArgs& a, cudaStream_t st) {
   if (a.n <= 32 || a.n > 128 || a.F < 1 || a.F > 4) return PACOH_ERR_UNSUPPORTED;
   if (a.P > 65535) return PACOH_ERR_UNSUPPORTED;
-  static bool carveout_set = false;
-  if (!carveout_set) {   // 8 CTAs / SM need 8 x 17 KB of shared memory: ask for the large carve-out (L1 is not used)
-    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    carveout_set = true;
-  }
+  const bool rag = a.task_n != nullptr;
+  const dim3 grid(a.n <= 64 ? (a.T + 1) / 2 : a.T, a.P);
+  // 8 CTAs / SM need 8 x 17 KB of shared memory: ask for the large carve-out (L1 is not used)
+#define PACOH_GPTC_LAUNCH(FT_, MT_, RAG_)                                                                               \
+  do {                                                                                                                  \
+    static bool once = false;                                                                                           \
+    if (!once) {                                                                                                        \
+      PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_tc_kernel<FT_, MT_, RAG_>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                            cudaSharedmemCarveoutMaxShared));                                           \
+      once = true;                                                                                                      \
+    }                                                                                                                   \
+    gp_tc_kernel<FT_, MT_, RAG_><<<grid, kGT, 0, st>>>(a);                                                              \
+  } while (0)
   if (a.n <= 64) {
-    const dim3 grid((a.T + 1) / 2, a.P);
-    if (a.F <= 2) gp_tc_kernel<2, 2><<<grid, kGT, 0, st>>>(a);
-    else gp_tc_kernel<4, 2><<<grid, kGT, 0, st>>>(a);
+    if (a.F <= 2) { if (rag) PACOH_GPTC_LAUNCH(2, 2, true); else PACOH_GPTC_LAUNCH(2, 2, false); }
+    else { if (rag) PACOH_GPTC_LAUNCH(4, 2, true); else PACOH_GPTC_LAUNCH(4, 2, false); }
   } else {
-    const dim3 grid(a.T, a.P);
-    if (a.F <= 2) gp_tc_kernel<2, 1><<<grid, kGT, 0, st>>>(a);
-    else gp_tc_kernel<4, 1><<<grid, kGT, 0, st>>>(a);
+    if (a.F <= 2) { if (rag) PACOH_GPTC_LAUNCH(2, 1, true); else PACOH_GPTC_LAUNCH(2, 1, false); }
+    else { if (rag) PACOH_GPTC_LAUNCH(4, 1, true); else PACOH_GPTC_LAUNCH(4, 1, false); }
   }
+#undef PACOH_GPTC_LAUNCH
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

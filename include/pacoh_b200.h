@@ -192,6 +192,13 @@ int pacoh_adam_step(int64_t count, float* param, const float* grad, float grad_s
                     float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
 
 /*
+ * Host-only helper: the persistent schedule of the tensor-core MLP backward kernel (one CTA per SM per wave, the
+ * nets * P * ceil(points / 128) tiles cut into equal ranges): CTAs, tiles per CTA, and the number of partial-gradient
+ * slots a (net, particle) can be split into.  No device work; lets the schedule arithmetic be tested on a CPU-only host.
+ */
+int pacoh_mlp_bwd_schedule(int32_t P, int32_t nets, int64_t points, int32_t* grid, int32_t* tiles_per_cta, int32_t* slots);
+
+/*
  * Optional per-stage device timing of pacoh_meta_mll_fwd_bwd (used by bench.py for the per-kernel roofline):
  * enable, run calls, then read the accumulated milliseconds per stage since the last read
  * (stages: 0 mlp_fwd, 1 gp_mll, 2 mlp_bwd, 3 reductions).  Reading synchronises the recorded events.

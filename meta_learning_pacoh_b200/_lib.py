@@ -19,7 +19,7 @@ SVGD_RBF, SVGD_IMQ = 0, 1
 # every symbol include/pacoh_b200.h declares (tests/test_capi_symbols.py checks the header against this list)
 EXPORTED_SYMBOLS = [
     "pacoh_abi_version", "pacoh_last_error", "pacoh_param_count", "pacoh_hyper_prior_params",
-    "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_meta_mll_fwd_bwd_ragged", "pacoh_logprob_finalize", "pacoh_peer_allreduce_finalize", "pacoh_svgd_workspace_bytes",
+    "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_meta_mll_fwd_bwd_ragged", "pacoh_mlp_bwd_schedule", "pacoh_logprob_finalize", "pacoh_peer_allreduce_finalize", "pacoh_svgd_workspace_bytes",
     "pacoh_svgd_phi", "pacoh_svgd_kernel_matrix", "pacoh_svgd_phi_apply", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
     "pacoh_stage_timing_enable", "pacoh_stage_timing_read", "pacoh_gp_forward", "pacoh_gp_forward_workspace_bytes",
 ]
@@ -62,6 +62,8 @@ def _load():
     lib.pacoh_workspace_bytes.argtypes = [archp, i32, i32, i32]
     lib.pacoh_meta_mll_fwd_bwd.restype = ctypes.c_int
     lib.pacoh_meta_mll_fwd_bwd.argtypes = [archp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.pacoh_mlp_bwd_schedule.restype = ctypes.c_int
+    lib.pacoh_mlp_bwd_schedule.argtypes = [i32, i32, i64, vp, vp, vp]
     lib.pacoh_meta_mll_fwd_bwd_ragged.restype = ctypes.c_int
     lib.pacoh_meta_mll_fwd_bwd_ragged.argtypes = [archp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.pacoh_logprob_finalize.restype = ctypes.c_int

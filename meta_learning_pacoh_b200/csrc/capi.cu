@@ -391,6 +391,22 @@ extern "C" int pacoh_meta_mll_fwd_bwd_ragged(const pacoh_arch_t* arch, int32_t P
   return rc;
 }
 
+// Host-only: the persistent schedule of the tensor-core MLP backward kernel for a (P, nets, T * n)-point launch -- number
+// of CTAs, tiles per CTA and partial-gradient slots per (net, particle).  Exposed so that the schedule arithmetic can be
+// checked without a GPU (tests/test_host_logic.py); assumes 148 SMs when no device is present.
+extern "C" int pacoh_mlp_bwd_schedule(int32_t P, int32_t nets, int64_t points, int32_t* grid, int32_t* tiles_per_cta,
+                                      int32_t* slots) {
+  if (P < 1 || nets < 1 || nets > 2 || points < 1 || points > 0x7fffffff || !grid || !tiles_per_cta || !slots) {
+    set_error("pacoh_mlp_bwd_schedule: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  int g = 0, per = 0;
+  *slots = mlp_tc_bwd_slots(P, nets, (int)points, &g, &per);
+  *grid = g;
+  *tiles_per_cta = per;
+  return PACOH_OK;
+}
+
 extern "C" int64_t pacoh_gp_forward_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t npts) {
   Plan pl;
   int rc = make_plan(arch, P, 1, 1, &pl);

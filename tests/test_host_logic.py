@@ -98,3 +98,34 @@ def test_learner_classes_keep_reference_signatures():
     for cls in (GPRegressionMetaLearned, GPRegressionMetaLearnedSVGD, GPRegressionMetaLearnedVI):
         for m in ("meta_fit", "predict", "eval", "eval_datasets", "confidence_intervals"):
             assert callable(getattr(cls, m))
+
+
+def test_persistent_backward_schedule_covers_every_tile_once():
+    """The tensor-core MLP backward walks the linearised (net, particle, tile) space in equal per-CTA ranges and writes one
+    partial-gradient slot per (CTA, (net, particle)) it touches (mlp_tc_bwd.cu): restate the kernel's index arithmetic and
+    check coverage, slot uniqueness, the slot bound the workspace is sized with, and the accumulation-length bound."""
+    import ctypes
+    from meta_learning_pacoh_b200 import _lib
+    for P, nets, T, n in [(64, 2, 4096, 50), (64, 2, 512, 50), (10, 2, 20, 5), (1, 1, 5, 5), (3, 2, 7, 64), (8, 1, 256, 20),
+                          (64, 2, 16384, 50), (5, 2, 11, 128), (128, 2, 33, 37)]:
+        g, per, slots = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(_lib.lib.pacoh_mlp_bwd_schedule(P, nets, T * n, ctypes.byref(g), ctypes.byref(per), ctypes.byref(slots)))
+        grid, per_cta, slots = g.value, per.value, slots.value
+        tiles = (T * n + 127) // 128
+        total = nets * P * tiles
+        assert (grid - 1) * per_cta < total <= grid * per_cta
+        seen = np.zeros(total, dtype=np.int32)
+        used = set()
+        for cta in range(grid):
+            g0, g1 = cta * per_cta, min(total, (cta + 1) * per_cta)
+            while g0 < g1:
+                pn = g0 // tiles
+                t0, t1 = g0 - pn * tiles, min(g1, (pn + 1) * tiles) - pn * tiles
+                slot = cta - (pn * tiles) // per_cta
+                assert 0 <= slot < slots and (pn, slot) not in used
+                used.add((pn, slot))
+                seen[pn * tiles + t0:pn * tiles + t1] += 1
+                g0 += t1 - t0
+        assert (seen == 1).all()
+        assert per_cta <= max(6, 3 * 120 + 2)           # <= 120 tiles per warpgroup accumulator (3 warpgroups per CTA)
+

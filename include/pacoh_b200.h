@@ -68,7 +68,7 @@ int64_t pacoh_param_count(const pacoh_arch_t* arch);
 int pacoh_hyper_prior_params(const pacoh_arch_t* arch, float weight_prior_std, float bias_prior_std,
                              float* mu_host, float* sigma_host);
 
-/* Scratch bytes needed by pacoh_meta_logprob_fwd_bwd for P parameter vectors, T batch tasks of n points. */
+/* Scratch bytes needed by pacoh_meta_mll_fwd_bwd for P parameter vectors, T batch tasks of n points. */
 int64_t pacoh_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n);
 
 /*
@@ -206,6 +206,17 @@ int pacoh_mlp_bwd_schedule(int32_t P, int32_t nets, int64_t points, int32_t* gri
 #define PACOH_NUM_STAGES 4
 int pacoh_stage_timing_enable(int32_t on);
 int pacoh_stage_timing_read(float* ms_out, int32_t* calls_out);
+
+/*
+ * Diagnostics for the large-n path (64 < n <= 4096 points per task: blocked Cholesky / inverse on the tensor cores,
+ * csrc/gp_big.cu).  out[14] (host): [0] byte offset of the large-n scratch inside the workspace of
+ * pacoh_meta_mll_fwd_bwd (0 and all-zero when (n, F) takes a small-matrix kernel), [1] tiles per side, [2] padded n,
+ * [3] matrices per pass, then the byte offsets (relative to [0]) of: [4] L / U tiles (batch, npad, npad), [5] inverted
+ * diagonal tiles (batch, nb, 2, 128, 128), [6] scaled features, [7] residuals, [8] v = L^-1 r, [9] alphahat,
+ * [10] log2-det partials, [11] gradient partials, [12] per-matrix state, [13] total bytes.  Lets the tests compare the
+ * factors themselves with an fp64 Cholesky.
+ */
+int pacoh_debug_big_layout(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n, int64_t* out);
 
 /* FP32 FFMA micro-benchmark used by bench.py for the roofline denominator.  iters > 0: immediate-operand dependent
  * chains (the classic peak test); iters < 0: |iters| iterations of a GEMM-shaped body whose FFMAs read three distinct

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_meta_mll_fwd_bwd_ragged", "pacoh_mlp_bwd_schedule", "pacoh_logprob_finalize", "pacoh_peer_allreduce_finalize", "pacoh_svgd_workspace_bytes",
     "pacoh_svgd_phi", "pacoh_svgd_kernel_matrix", "pacoh_svgd_phi_apply", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
     "pacoh_stage_timing_enable", "pacoh_stage_timing_read", "pacoh_gp_forward", "pacoh_gp_forward_workspace_bytes",
+    "pacoh_debug_big_layout",
 ]
 
 
@@ -62,6 +63,8 @@ def _load():
     lib.pacoh_workspace_bytes.argtypes = [archp, i32, i32, i32]
     lib.pacoh_meta_mll_fwd_bwd.restype = ctypes.c_int
     lib.pacoh_meta_mll_fwd_bwd.argtypes = [archp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.pacoh_debug_big_layout.restype = ctypes.c_int
+    lib.pacoh_debug_big_layout.argtypes = [archp, i32, i32, i32, ctypes.POINTER(i64)]
     lib.pacoh_mlp_bwd_schedule.restype = ctypes.c_int
     lib.pacoh_mlp_bwd_schedule.argtypes = [i32, i32, i64, vp, vp, vp]
     lib.pacoh_meta_mll_fwd_bwd_ragged.restype = ctypes.c_int

@@ -125,11 +125,25 @@ static int launch_mlp_best(const MlpArgs& ma, int nets, int chunks, bool bwd, cu
   return launch_mlp_fast(ma, nets, chunks, bwd, st);
 }
 
+// n > 64 runs the blocked tensor-core Cholesky path (gp_big.cu).  PACOH_GP=tc128 keeps the in-place Gauss-Jordan
+// tensor-memory kernel for 64 < n <= 128 (faster, but only 5e-4-accurate gradients there: A/B measurements).
+bool gp_use_big(int n, int F) {
+  static int tc128 = -1;
+  if (tc128 < 0) {
+    const char* e = getenv("PACOH_GP");
+    tc128 = (e != nullptr && strcmp(e, "tc128") == 0) ? 1 : 0;
+  }
+  if (n <= 64 || F > 4) return false;
+  if (n <= kMaxGpN && tc128 == 1) return false;
+  return true;
+}
+
 struct Plan {
   ModelDev m;
   int Q, chunks, chunks_fwd;   // chunks: partial-gradient slots / grid.x of the chunked backward kernels; chunks_fwd: forward kernels
   bool mean_nn, kern_nn, mean_fast, kern_fast, fused;   // fused: one launch covers both nets
-  size_t off_mean, off_feat, off_dmean, off_dfeat, off_mll, off_hyp, off_pmean, off_pkern, off_gen, total;
+  size_t off_mean, off_feat, off_dmean, off_dfeat, off_mll, off_hyp, off_pmean, off_pkern, off_gen, off_big, big_bytes, total;
+  bool big;                    // the GP stage runs on the blocked large-n path
 };
 
 static size_t align_up(size_t v) { return (v + 63) & ~(size_t)63; }
@@ -138,7 +152,8 @@ static int make_plan(const pacoh_arch_t* arch, int P, int T, int n, Plan* pl) {
   if (!build_model(arch, &pl->m)) { set_error("invalid architecture descriptor"); return PACOH_ERR_INVALID; }
   if (P < 1 || T < 1 || n < 1) { set_error("P, T, n must be positive"); return PACOH_ERR_INVALID; }
   const ModelDev& m = pl->m;
-  if (n > kMaxGpN) { set_error("n=%d > %d points per task is not implemented yet (blocked large-n path)", n, kMaxGpN); return PACOH_ERR_UNSUPPORTED; }
+  pl->big = gp_use_big(n, m.F);
+  if (n > (pl->big ? kMaxBigN : kMaxGpN)) { set_error("n=%d points per task with feature dim %d: not supported (max %d)", n, m.F, pl->big ? kMaxBigN : kMaxGpN); return PACOH_ERR_UNSUPPORTED; }
   if (m.F > kMaxGpF) { set_error("feature dim %d > %d not supported", m.F, kMaxGpF); return PACOH_ERR_UNSUPPORTED; }
   pl->Q = T * n;
   pl->mean_nn = m.mean_kind == PACOH_MEAN_NN;
@@ -166,6 +181,8 @@ static int make_plan(const pacoh_arch_t* arch, int P, int T, int n, Plan* pl) {
   if (pl->mean_nn && !pl->mean_fast) gen = std::max(gen, mlp_generic_scratch_floats(m.mean, P, pl->Q));
   if (pl->kern_nn && !pl->kern_fast) gen = std::max(gen, mlp_generic_scratch_floats(m.kern, P, pl->Q));
   pl->off_gen = take(gen);
+  pl->big_bytes = pl->big ? gp_big_workspace_bytes(n, (long long)P * T) : 0;
+  pl->off_big = take((pl->big_bytes + 3) / 4);
   pl->total = off;
   return PACOH_OK;
 }
@@ -294,6 +311,21 @@ extern "C" int64_t pacoh_workspace_bytes(const pacoh_arch_t* arch, int32_t P, in
   return (int64_t)(pl.total * sizeof(float));
 }
 
+// Diagnostics: where the large-n path keeps its factors inside the caller's workspace (tests read L / U back).
+extern "C" int pacoh_debug_big_layout(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n, int64_t* out) {
+  Plan pl;
+  int rc = make_plan(arch, P, T, n, &pl);
+  if (rc != PACOH_OK) return rc;
+  if (!out) { set_error("pacoh_debug_big_layout: null output"); return PACOH_ERR_INVALID; }
+  for (int i = 0; i < 14; ++i) out[i] = 0;
+  if (!pl.big) return PACOH_OK;
+  long long tmp[13];
+  gp_big_layout_debug(n, (long long)P * T, tmp);
+  out[0] = (int64_t)(pl.off_big * sizeof(float));
+  for (int i = 0; i < 13; ++i) out[i + 1] = tmp[i];
+  return PACOH_OK;
+}
+
 extern "C" int pacoh_meta_mll_fwd_bwd(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n, const float* theta,
                                       const float* x, const float* y, const int32_t* task_idx, float* mll, float* mll_sum,
                                       float* dtheta_lik, int32_t* info, void* workspace, int64_t workspace_bytes,
@@ -367,7 +399,8 @@ extern "C" int pacoh_meta_mll_fwd_bwd_ragged(const pacoh_arch_t* arch, int32_t P
   ga.mean_kind = m.mean_kind; ga.covar_kind = m.covar_kind; ga.has_oscale = m.has_oscale;
   ga.noise_floor = m.noise_floor;
   ga.off_ls = m.off_ls; ga.off_noise = m.off_noise; ga.off_oscale = m.off_oscale; ga.off_const_mean = m.off_const_mean;
-  if ((rc = launch_gp_mll(ga, st)) != PACOH_OK) { if (rc == PACOH_ERR_UNSUPPORTED) set_error("GP kernel: unsupported n=%d / F=%d", n, m.F); return rc; }
+  rc = pl.big ? launch_gp_mll_big(ga, ws + pl.off_big, pl.big_bytes, st) : launch_gp_mll(ga, st);
+  if (rc != PACOH_OK) { if (rc == PACOH_ERR_UNSUPPORTED) set_error("GP kernel: unsupported n=%d / F=%d", n, m.F); return rc; }
 
   stage_mark(2, st);
   // The (P, T) -> (P) reduction of the per-task values and hyper-parameter gradients only needs the GP kernel's output

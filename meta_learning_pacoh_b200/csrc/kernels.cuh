@@ -42,10 +42,16 @@ struct GpArgs {
   int off_ls, off_noise, off_oscale, off_const_mean;
 };
 constexpr int kMaxGpN = 128;   // register kernel: n <= 64; tensor-memory kernel: 32 < n <= 128 (feature dim <= 4)
+constexpr int kMaxBigN = 4096; // blocked tensor-core Cholesky path (gp_big.cu): 64 < n <= 4096, feature dim <= 4
 constexpr int kMaxGpF = 16;    // feature dim
 __host__ __device__ inline int gp_hyp_stride(int F) { return F + 3; }
 int launch_gp_mll(const GpArgs& a, cudaStream_t st);
 int launch_gp_mll_tc(const GpArgs& a, cudaStream_t st);   // gp_tc.cu: tcgen05 / tensor-memory version, 32 < n <= 64, F <= 4
+// gp_big.cu: blocked Cholesky / inverse on the tensor cores for n > 64 (BASELINE config #5); scratch from the caller
+size_t gp_big_workspace_bytes(int n, long long matrices);
+int launch_gp_mll_big(const GpArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+void gp_big_layout_debug(int n, long long matrices, long long* out);
+bool gp_use_big(int n, int F);   // capi.cu: which path a (n, F) problem takes
 
 // ---- reductions / elementwise (finalize.cu) ------------------------------------------------------------
 int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,

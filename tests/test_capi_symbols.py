@@ -67,8 +67,10 @@ def test_argument_validation_and_workspace_sizes():
     assert nbytes < 2 * 1024 ** 3
     assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 0, 4, 5) == _lib.PACOH_ERR_INVALID
     assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 2, 4, 128) > 0              # extended range: one matrix per CTA
-    assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 2, 4, 129) == _lib.PACOH_ERR_UNSUPPORTED
-    assert b"not implemented" in _lib.lib.pacoh_last_error()
+    assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 2, 4, 129) > 2 * 4 * 256 * 256 * 4    # blocked large-n path: L / U tiles
+    assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 1, 8, 2048) > 8 * 2048 * 2048 * 4      # BASELINE config #5
+    assert _lib.lib.pacoh_workspace_bytes(ctypes.byref(a), 2, 4, 4097) == _lib.PACOH_ERR_UNSUPPORTED
+    assert b"not supported" in _lib.lib.pacoh_last_error()
     bad = eng.GPArch(1).c_struct()
     bad.mean_kind = 7
     assert _lib.lib.pacoh_param_count(ctypes.byref(bad)) == _lib.PACOH_ERR_INVALID

@@ -27,6 +27,8 @@
 #include <cuda.h>
 #include <math_constants.h>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -60,6 +62,27 @@ constexpr uint32_t kTmemAcol = 256;     // D0 [0,128) | D1 [128,256) | A stages 
 enum { M_DIAG = 0, M_PANEL = 1, M_UINV = 2, M_GRAD = 3 };
 
 __device__ __forceinline__ float ex2b(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 3xTF32 operand split with round-to-nearest parts: v = hi + lo + O(2^-23 |v|), errors symmetric around zero (a
+// truncating split leaves every operand short by up to 2^-21 |v| with the sign of v, a bias that sums coherently over
+// K and is what trace-like contractions of Khat^-1 are most sensitive to).
+// (cvt.rna.tf32.f32 is emulated with ~5 instructions on sm_100; adding half an ulp before the mask does the same in 2 for
+// finite values.  A lo part only needs the "+ half ulp": the tensor core's own truncation completes the rounding.)
+__device__ __forceinline__ float rn_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float pre_round(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
+// B operand: the raw fp32 tile is the hi part (the tensor core truncates it), so lo = v - trunc(v), rounded to tf32
+__device__ __forceinline__ float lo_of_raw(float v) { return pre_round(v - tf32_hi(v)); }
+
+// Khat entry: rho 2^(-|du|^2) (e0 = log2 rho, or -inf for a padding row); one definition so that the factorisation and
+// the residual of the iterative refinement see bit-identical matrices
+__device__ __forceinline__ float khat_entry(const float4& ur, const float4& uc, float e0) {
+  float e = e0;
+  { const float du = ur.x - uc.x; e = fmaf(-du, du, e); }
+  { const float du = ur.y - uc.y; e = fmaf(-du, du, e); }
+  { const float du = ur.z - uc.z; e = fmaf(-du, du, e); }
+  { const float du = ur.w - uc.w; e = fmaf(-du, du, e); }
+  return ex2b(e);
+}
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -100,8 +123,12 @@ struct BigArgs {
   float* rbuf;                 // (B, npad)  residuals y - m (0 on padding rows)
   float* vbuf;                 // (B, npad)  v = L^-1 r
   float* abuf;                 // (B, npad)  alphahat = Khat^-1 r
+  float* wbuf;                 // (B, npad)  scratch of the iterative refinement
   float* ldet;                 // (B, nb_max) sum of log2 L_ii per diagonal tile
-  float* part;                 // (B, nb_max, 8) per-block-row partial sums of the gradient contraction
+  float* part;                 // (B, nb_max, 12) per-tile partial sums: quad tot, -, trace, sum beta, S2[4], sum S1[4]
+  float* rowpart;              // (B, npad, 8)   per-row sums over the tiles of the row's own block row (+ diagonal of Khat^-1)
+  float* colpart;              // (B, npairs, 128, 4) column sums of the tiles (a, b), b < a: contributions to the rows of block b
+  int npairs;                  // nb_max (nb_max - 1) / 2
   BigMat* mat;                 // (B)
   const int* list;             // retry passes: indices of the matrices to redo (nullptr: all B matrices)
   const int* count;            //               and how many
@@ -305,11 +332,13 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
     return it;
   };
   // number of sub-tiles of an item and K blocks of a sub-tile
-  auto nsub_of = [&](const Item& it) { return MODE == M_GRAD ? it.nbm : 1; };
+  // GRAD: block row a computes the tiles (a, b) for b <= a only (Khat^-1 is symmetric): every tile feeds the rows of
+  // block a directly and, for b < a, the rows of block b through column sums
+  auto nsub_of = [&](const Item& it) { return MODE == M_GRAD ? it.ti + 1 : 1; };
   auto nblk_of = [&](const Item& it, int sub) {
     if (MODE == M_DIAG || MODE == M_PANEL) return step;
     if (MODE == M_UINV) return step;
-    return it.nbm - max(it.ti, sub);
+    return it.nbm - it.ti;
   };
 
   if (warp == 8) {
@@ -341,7 +370,7 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
               if (j == it.ti) { a_sb = true; a_z = sbz + 2 * it.ti + 1; } else { a_row = it.ti * NB; a_col = j * NB; }
               b_row = it.tj * NB; b_col = j * NB;
             } else {
-              const int mm = max(it.ti, sub) + q;
+              const int mm = it.ti + q;
               if (mm == it.ti) { a_sb = true; a_z = sbz + 2 * it.ti + 1; } else { a_row = it.ti * NB; a_col = mm * NB; }
               if (mm == sub) { b_sb = true; b_z = sbz + 2 * sub + 1; } else { b_row = sub * NB; b_col = mm * NB; }
             }
@@ -410,6 +439,9 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
     float* misc = reinterpret_cast<float*>(smem + kOffMisc);
     uint32_t g = 0, bb = 0;
     float acc[64];
+    int swz[4];                                             // byte offsets of this thread's four 16-byte pieces in a SWIZZLE_128B tile
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) swz[j4] = r * 128 + (((4 * h + j4) ^ (r & 7)) << 4);
 
     auto flush = [&](uint32_t b) {       // acc += accumulator of K block b (this thread's 64 columns of its row)
       const uint32_t d = b & 1;
@@ -435,8 +467,9 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
       const bool rvalid = row < mt.n;
       const float4 urow = a.ubuf[vecoff + row];
       // GRAD: per-row accumulators over the whole block row
-      float Sk = 0.0f, S1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, trc = 0.0f, alpha_r = 0.0f, beta_r = 0.0f;
+      float S1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, trc = 0.0f, alpha_r = 0.0f, beta_r = 0.0f;
       if (MODE == M_GRAD) { alpha_r = a.abuf[vecoff + row]; beta_r = alpha_r / mt.tot; }
+      const float inv_tot = 1.0f / mt.tot;
       float tdot = 0.0f;                                    // DIAG: sum_j L_kj v_j for this row (this thread's k-half)
       const int ns = nsub_of(it);
       for (int sub = 0; sub < ns; ++sub) {
@@ -465,8 +498,7 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
-                const int j = 4 * h + j4;
-                const float4 v = *reinterpret_cast<const float4*>(rawA + r * 128 + ((j ^ (r & 7)) << 4));
+                const float4 v = *reinterpret_cast<const float4*>(rawA + swz[j4]);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
                 if (MODE == M_DIAG) {
                   const float4 w = __ldg(reinterpret_cast<const float4*>(vsrc + c * KC + 4 * j4));
@@ -474,7 +506,7 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float hv = tf32_hi(vv[e]);
+                  const float hv = rn_tf32(vv[e]);
                   hi[4 * j4 + e] = __float_as_uint(hv);
                   lo[4 * j4 + e] = __float_as_uint(vv[e] - hv);
                 }
@@ -486,9 +518,9 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
             // B: lo part of row r, same k-half, written beside the raw tile at the same swizzled position
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const int off = r * 128 + (((4 * h + j4) ^ (r & 7)) << 4);
+              const int off = swz[j4];
               const float4 v = *reinterpret_cast<const float4*>(rawB + off);
-              *reinterpret_cast<float4*>(loB + off) = make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+              *reinterpret_cast<float4*>(loB + off) = make_float4(lo_of_raw(v.x), lo_of_raw(v.y), lo_of_raw(v.z), lo_of_raw(v.w));
             }
             tmem_st_wait();
             fence_before_sync();
@@ -507,13 +539,7 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 64; ++i) {
             const int cc = 64 * h + i;
-            const float4 uc = ucol[cc];
-            float e = e0;
-            { const float du = urow.x - uc.x; e = fmaf(-du, du, e); }
-            { const float du = urow.y - uc.y; e = fmaf(-du, du, e); }
-            { const float du = urow.z - uc.z; e = fmaf(-du, du, e); }
-            { const float du = urow.w - uc.w; e = fmaf(-du, du, e); }
-            float kv = ex2b(e);
+            float kv = khat_entry(urow, ucol[cc], e0);
             if (MODE == M_DIAG && cc == r) kv = 1.0f;
             acc[i] = kv - acc[i];
           }
@@ -536,7 +562,7 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                  const float v = acc[32 * (c & 1) + 16 * q2 + e], hv = tf32_hi(v);
+                  const float v = acc[32 * (c & 1) + 16 * q2 + e], hv = rn_tf32(v);
                   hi[e] = __float_as_uint(hv);
                   lo[e] = __float_as_uint(v - hv);
                 }
@@ -547,9 +573,9 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
             }
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const int off = r * 128 + (((4 * h + j4) ^ (r & 7)) << 4);
+              const int off = swz[j4];
               const float4 v = *reinterpret_cast<const float4*>(rawB + off);
-              *reinterpret_cast<float4*>(loB + off) = make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+              *reinterpret_cast<float4*>(loB + off) = make_float4(lo_of_raw(v.x), lo_of_raw(v.y), lo_of_raw(v.z), lo_of_raw(v.w));
             }
             tmem_st_wait();
             fence_before_sync();
@@ -621,66 +647,88 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
         }
 
         if (MODE == M_GRAD) {
-          // ------------------------------------------------------------ gradient contraction with the row of Khat^-1
+          // ------------------------------------------------------------ gradient contraction with the tile of Khat^-1:
+          //   w_rc = (alphahat_r alphahat_c / tot - Khat^-1_rc) k_rc          (bit-symmetric in r <-> c)
+          //   rows of block a:     S1_r += sum_c w_rc (u_r - u_c)
+          //   rows of block b < a: S1_c += sum_r w_rc (u_c - u_r)             (column sums of the same products)
+          const bool offdiag = sub < it.ti;
+          const int F = a.g.F;
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int cc = 64 * h + i;
-            const float4 uc = ucol[cc];
-            const float d0 = urow.x - uc.x, d1 = urow.y - uc.y, d2 = urow.z - uc.z, d3 = urow.w - uc.w;
-            const float e = fmaf(-d0, d0, fmaf(-d1, d1, fmaf(-d2, d2, -d3 * d3)));
-            const float wv = fmaf(beta_r, acolv[cc], -acc[i]) * ex2b(e);
-            Sk += wv;
-            S1[0] = fmaf(wv, d0, S1[0]); S1[1] = fmaf(wv, d1, S1[1]); S1[2] = fmaf(wv, d2, S1[2]); S1[3] = fmaf(wv, d3, S1[3]);
-            if (sub == it.ti && cc == r) trc = fmaf(beta_r, alpha_r, -acc[i]);
+          for (int g2 = 0; g2 < 2; ++g2) {
+            float x0[32], x1[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int cc = 64 * h + 32 * g2 + i;
+              const float4 uc = ucol[cc];
+              const float d0 = urow.x - uc.x, d1 = urow.y - uc.y, d2 = urow.z - uc.z, d3 = urow.w - uc.w;
+              const float e = fmaf(-d0, d0, fmaf(-d1, d1, fmaf(-d2, d2, -d3 * d3)));
+              const float wv = fmaf(alpha_r * acolv[cc], inv_tot, -acc[32 * g2 + i]) * ex2b(e);
+              S1[0] = fmaf(wv, d0, S1[0]); S1[1] = fmaf(wv, d1, S1[1]); S1[2] = fmaf(wv, d2, S1[2]); S1[3] = fmaf(wv, d3, S1[3]);
+              x0[i] = wv * d0; x1[i] = wv * d1;
+              if (!offdiag && cc == r) trc = fmaf(alpha_r * alpha_r, inv_tot, -acc[32 * g2 + i]);
+            }
+            if (offdiag) {
+              // column sums over the warp's 32 rows: transpose-reduce (31 shuffles per 32 columns), lane l <- column l
+#pragma unroll
+              for (int f = 0; f < 4; ++f) {
+                if (f >= F) break;
+                float v[32];
+                if (f < 2) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = f == 0 ? x0[i] : x1[i];
+                } else {        // features 2, 3 (rare): recompute the products
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const int cc = 64 * h + 32 * g2 + i;
+                    const float4 uc = ucol[cc];
+                    const float d0 = urow.x - uc.x, d1 = urow.y - uc.y, d2 = urow.z - uc.z, d3 = urow.w - uc.w;
+                    const float e = fmaf(-d0, d0, fmaf(-d1, d1, fmaf(-d2, d2, -d3 * d3)));
+                    const float wv = fmaf(alpha_r * acolv[cc], inv_tot, -acc[32 * g2 + i]) * ex2b(e);
+                    v[i] = wv * (f == 2 ? d2 : d3);
+                  }
+                }
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+                  const bool up = (lane & sft) != 0;
+#pragma unroll
+                  for (int i = 0; i < sft; ++i) {
+                    const float send = up ? v[i] : v[i + sft];
+                    const float keep = up ? v[i + sft] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                  }
+                }
+                // T scratch: [warp][g2][f][lane]
+                T[((warp * 2 + g2) * 4 + f) * 32 + lane] = v[0];
+              }
+            }
+          }
+          if (offdiag) {
+            conv_sync();
+            // column c = 64 h' + 32 g2 + l of tile `sub`: sum over the four warps with the same h' (fixed order), negated
+            for (int o = tid; o < NB * 4; o += kConv) {
+              const int cc = o >> 2, f = o & 3;
+              float sv = 0.0f;
+              if (f < F) {
+                const int hh = cc >> 6, g2 = (cc >> 5) & 1, l = cc & 31;
+                const float* src = T + ((hh * 4 * 2 + g2) * 4 + f) * 32 + l;
+                sv = -((src[0] + src[2 * 4 * 32]) + (src[2 * 2 * 4 * 32] + src[3 * 2 * 4 * 32]));
+              }
+              a.colpart[(((size_t)it.m * a.npairs + (size_t)it.ti * (it.ti - 1) / 2 + sub) * NB + cc) * 4 + f] = sv;
+            }
           }
         }
       }
 
       if (MODE == M_GRAD) {
-        // combine the two column halves of every row, write the per-point gradients, reduce the block row's partial sums
+        // the row sums of this block row (two column halves per row) and the diagonal of Khat^-1
         conv_sync();
-        if (h == 1) { float* o = T + r * 8; o[0] = Sk; o[1] = S1[0]; o[2] = S1[1]; o[3] = S1[2]; o[4] = S1[3]; o[5] = trc; }
+        if (h == 1) { float* o = T + r * 8; o[1] = S1[0]; o[2] = S1[1]; o[3] = S1[2]; o[4] = S1[3]; o[5] = trc; }
         conv_sync();
-        float red[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (h == 0) {
           const float* o = T + r * 8;
-          Sk += o[0]; S1[0] += o[1]; S1[1] += o[2]; S1[2] += o[3]; S1[3] += o[4]; trc += o[5];
-          const GpArgs& ga = a.g;
-          const float inv_n = 1.0f / (float)mt.n;
-          const int F = ga.F;
-          if (row < ga.n) {
-            const size_t qpt = (size_t)mt.p * ga.T * ga.n + (size_t)mt.t * ga.n + row;
-            const bool failed = mt.status < 0;
-            if (ga.dmean != nullptr) ga.dmean[qpt] = (rvalid && !failed) ? beta_r * inv_n : 0.0f;
-            if (ga.dfeat != nullptr) {
-              const float* th = ga.theta + (size_t)mt.p * ga.D;
-              for (int f = 0; f < F; ++f) {
-                const float sc = kCB / softplus_f(__ldg(th + ga.off_ls + f));     // scaled inverse lengthscale
-                ga.dfeat[qpt * F + f] = (rvalid && !failed) ? -mt.rho * inv_n * sc / (kCB * kCB) * S1[f] : 0.0f;
-              }
-            }
-          }
-          const float4 u0 = a.ubuf[vecoff];
-          red[0] = rvalid ? a.rbuf[vecoff + row] * alpha_r : 0.0f;      // quad * tot
-          red[1] = rvalid ? Sk : 0.0f;
-          red[2] = rvalid ? trc : 0.0f;
-          red[3] = rvalid ? beta_r : 0.0f;
-          red[4] = rvalid ? 2.0f * (urow.x - u0.x) * S1[0] : 0.0f;
-          red[5] = rvalid ? 2.0f * (urow.y - u0.y) * S1[1] : 0.0f;
-          red[6] = rvalid ? 2.0f * (urow.z - u0.z) * S1[2] : 0.0f;
-          red[7] = rvalid ? 2.0f * (urow.w - u0.w) * S1[3] : 0.0f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) red[i] = warp_sum(red[i]);
-        }
-        conv_sync();
-        if (h == 0 && lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) T[1024 + warp * 8 + i] = red[i];
-        }
-        conv_sync();
-        if (tid < 8) {
-          const float v = (T[1024 + tid] + T[1024 + 8 + tid]) + (T[1024 + 16 + tid] + T[1024 + 24 + tid]);
-          a.part[((size_t)it.m * a.nb_max + it.ti) * 8 + tid] = v;
+          float* dst = a.rowpart + (vecoff + row) * 8;
+          *reinterpret_cast<float4*>(dst) = make_float4(S1[0] + o[1], S1[1] + o[2], S1[2] + o[3], S1[3] + o[4]);
+          dst[4] = trc + o[5];
         }
       }
     }
@@ -749,22 +797,149 @@ __global__ void big_retry_kernel(BigArgs a, int* list_out, int* count_out) {
   list_out[atomicAdd(count_out, 1)] = m;
 }
 
-// alphahat = U v: one CTA per (matrix, block row a), warp per row, lanes over the columns >= the row's block.
-__global__ void big_alpha_kernel(BigArgs a) {
+// y (+)= U x: one CTA per (matrix, block row a), warp per row, lanes over the columns >= the row's block.
+// alphahat = U v, and the correction U (U^T r') of the iterative refinement.
+__global__ void big_ux_kernel(BigArgs a, const float* __restrict__ xin, float* __restrict__ yout, int add) {
   const int m = blockIdx.x / a.nb_max, ta = blockIdx.x % a.nb_max;
   const BigMat mt = a.mat[m];
   if (ta >= mt.nb) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* v = a.vbuf + (size_t)m * a.npad;
+  const float* v = xin + (size_t)m * a.npad;
   const float* Ud = a.SB + (((size_t)m * a.nb_max + ta) * 2 + 1) * NB * NB;
   for (int rr = warp; rr < NB; rr += nw) {
     const int row = ta * NB + rr;
-    float s = 0.0f;
-    for (int c = lane; c < NB; c += 32) s = fmaf(Ud[rr * NB + c], v[ta * NB + c], s);
+    double s = 0.0;
+    for (int c = lane; c < NB; c += 32) s += (double)(Ud[rr * NB + c] * v[ta * NB + c]);
     const float* Urow = a.Lbuf + ((size_t)m * a.npad + row) * a.npad;
-    for (int c = (ta + 1) * NB + lane; c < mt.nb * NB; c += 32) s = fmaf(Urow[c], v[c], s);
-    s = warp_sum(s);
-    if (lane == 0) a.abuf[(size_t)m * a.npad + row] = s;
+    for (int c = (ta + 1) * NB + lane; c < mt.nb * NB; c += 32) s += (double)(Urow[c] * v[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      float* y = yout + (size_t)m * a.npad + row;
+      *y = add ? (float)((double)*y + s) : (float)s;
+    }
+  }
+}
+
+// w = U^T x = L^-1 x: one CTA per (matrix, block column b), thread per column, rows <= the column.
+__global__ void big_utx_kernel(BigArgs a, const float* __restrict__ xin, float* __restrict__ wout) {
+  __shared__ float xs[NB];
+  const int m = blockIdx.x / a.nb_max, tb = blockIdx.x % a.nb_max;
+  const BigMat mt = a.mat[m];
+  if (tb >= mt.nb) return;
+  const int c = threadIdx.x;
+  double s = 0.0;
+  for (int ta = 0; ta <= tb; ++ta) {
+    __syncthreads();
+    xs[c] = xin[(size_t)m * a.npad + ta * NB + c];
+    __syncthreads();
+    if (ta < tb) {
+      const float* U = a.Lbuf + ((size_t)m * a.npad + (size_t)ta * NB) * a.npad + (size_t)tb * NB + c;
+      for (int rr = 0; rr < NB; ++rr) s += (double)(U[(size_t)rr * a.npad] * xs[rr]);
+    } else {
+      const float* Ud = a.SB + (((size_t)m * a.nb_max + tb) * 2 + 1) * NB * NB + c;
+      for (int rr = 0; rr <= c; ++rr) s += (double)(Ud[rr * NB] * xs[rr]);
+    }
+  }
+  wout[(size_t)m * a.npad + tb * NB + c] = (float)s;
+}
+
+// r' = r - Khat alphahat with Khat regenerated from the features (bit-identical to the factorised matrix), fp64
+// accumulation: one CTA per (matrix, block row), thread per row.  One step of iterative refinement brings alphahat
+// from the accuracy of the explicit inverse U (1e-5 .. 1e-4 at n = 2048) to that of a backward-stable fp32 solve.
+__global__ void big_resid_kernel(BigArgs a, float* __restrict__ rout) {
+  __shared__ float4 us[NB];
+  __shared__ float as[NB];
+  const int m = blockIdx.x / a.nb_max, ta = blockIdx.x % a.nb_max;
+  const BigMat mt = a.mat[m];
+  if (ta >= mt.nb) return;
+  const int tid = threadIdx.x, row = ta * NB + tid;
+  const size_t vecoff = (size_t)m * a.npad;
+  const float4 ur = a.ubuf[vecoff + row];
+  const bool rvalid = row < mt.n;
+  const float e0 = rvalid ? mt.lg2rho : -CUDART_INF_F;
+  double s = 0.0;
+  for (int tb = 0; tb < mt.nb; ++tb) {
+    __syncthreads();
+    us[tid] = a.ubuf[vecoff + tb * NB + tid];
+    as[tid] = a.abuf[vecoff + tb * NB + tid];
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < NB; ++c) {
+      float kv = khat_entry(ur, us[c], e0);
+      if (tb == ta && c == tid) kv = 1.0f;
+      s += (double)(kv * as[c]);
+    }
+  }
+  rout[vecoff + row] = rvalid ? (float)((double)a.rbuf[vecoff + row] - s) : 0.0f;
+}
+
+// Per (matrix, tile t), thread per row: total S1 = own block row's sums + the column sums of the tiles (a, t), a > t;
+// per-point gradients dmean / dfeat and the tile's partial sums for the hyper-parameter gradients.
+__global__ void big_gradfin_kernel(BigArgs a) {
+  __shared__ float sred[4][12];
+  const int m = blockIdx.x / a.nb_max, tt = blockIdx.x % a.nb_max;
+  const BigMat mt = a.mat[m];
+  if (tt >= mt.nb) return;
+  const int tid = threadIdx.x, row = tt * NB + tid, warp = tid >> 5, lane = tid & 31;
+  const size_t vecoff = (size_t)m * a.npad;
+  const bool rvalid = row < mt.n;
+  const float* rp = a.rowpart + (vecoff + row) * 8;
+  float4 S = *reinterpret_cast<const float4*>(rp);
+  const float trc = rp[4];
+  for (int ta = tt + 1; ta < mt.nb; ++ta) {
+    const float4 c = *reinterpret_cast<const float4*>(a.colpart + (((size_t)m * a.npairs + (size_t)ta * (ta - 1) / 2 + tt) * NB + tid) * 4);
+    S.x += c.x; S.y += c.y; S.z += c.z; S.w += c.w;
+  }
+  const float S1[4] = {S.x, S.y, S.z, S.w};
+  *reinterpret_cast<float4*>(a.rowpart + (vecoff + row) * 8) = S;         // total, for big_dfeat_kernel
+  const float alpha_r = a.abuf[vecoff + row], beta_r = alpha_r / mt.tot;
+  const float4 urow = a.ubuf[vecoff + row], u0 = a.ubuf[vecoff];
+  float red[12];
+  red[0] = rvalid ? a.rbuf[vecoff + row] * alpha_r : 0.0f;      // quad * tot
+  red[1] = 0.0f;
+  red[2] = rvalid ? trc : 0.0f;
+  red[3] = rvalid ? beta_r : 0.0f;
+  red[4] = rvalid ? 2.0f * (urow.x - u0.x) * S1[0] : 0.0f;
+  red[5] = rvalid ? 2.0f * (urow.y - u0.y) * S1[1] : 0.0f;
+  red[6] = rvalid ? 2.0f * (urow.z - u0.z) * S1[2] : 0.0f;
+  red[7] = rvalid ? 2.0f * (urow.w - u0.w) * S1[3] : 0.0f;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) red[8 + f] = rvalid ? S1[f] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) red[i] = warp_sum(red[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sred[warp][i] = red[i];
+  }
+  __syncthreads();
+  if (tid < 12) a.part[((size_t)m * a.nb_max + tt) * 12 + tid] = (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
+}
+
+// Per (matrix, tile), thread per row: per-point gradients dmean / dfeat.  sum_a S1_a = 0 exactly (the kernel is invariant
+// to a common shift of the features); the rounding residue of the matrix-wide sum is removed here, which projects the
+// feature gradient back onto that invariance (the kernel net's output-bias gradient is this sum over all points).
+__global__ void big_dfeat_kernel(BigArgs a) {
+  const int m = blockIdx.x / a.nb_max, tt = blockIdx.x % a.nb_max;
+  const BigMat mt = a.mat[m];
+  if (tt >= mt.nb) return;
+  const int tid = threadIdx.x, row = tt * NB + tid;
+  const GpArgs& ga = a.g;
+  if (row >= ga.n) return;
+  const size_t vecoff = (size_t)m * a.npad;
+  const bool ok = row < mt.n && mt.status >= 0;
+  const float inv_n = 1.0f / (float)mt.n;
+  const size_t qpt = (size_t)mt.p * ga.T * ga.n + (size_t)mt.t * ga.n + row;
+  if (ga.dmean != nullptr) ga.dmean[qpt] = ok ? a.abuf[vecoff + row] / mt.tot * inv_n : 0.0f;
+  if (ga.dfeat != nullptr) {
+    const float* th = ga.theta + (size_t)mt.p * ga.D;
+    const float* S1 = a.rowpart + (vecoff + row) * 8;
+    for (int f = 0; f < ga.F; ++f) {
+      float tot = 0.0f;
+      for (int tb = 0; tb < mt.nb; ++tb) tot += a.part[((size_t)m * a.nb_max + tb) * 12 + 8 + f];
+      const float sc = kCB / softplus_f(__ldg(th + ga.off_ls + f));     // scaled inverse lengthscale
+      ga.dfeat[qpt * ga.F + f] = ok ? -mt.rho * inv_n * sc / (kCB * kCB) * (S1[f] - tot * inv_n) : 0.0f;
+    }
   }
 }
 
@@ -785,7 +960,7 @@ __global__ void big_finish_kernel(BigArgs a) {
   }
   float red[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ld2 = 0.0f;
   for (int tb = 0; tb < mt.nb; ++tb) {
-    for (int i = 0; i < 8; ++i) red[i] += a.part[((size_t)m * a.nb_max + tb) * 8 + i];
+    for (int i = 0; i < 8; ++i) red[i] += a.part[((size_t)m * a.nb_max + tb) * 12 + i];
     ld2 += a.ldet[(size_t)m * a.nb_max + tb];
   }
   const float n = (float)mt.n, inv_n = 1.0f / n, inv_tot = 1.0f / mt.tot;
@@ -798,7 +973,10 @@ __global__ void big_finish_kernel(BigArgs a) {
     hyp[f] = mt.rho * inv_n * red[4 + f] * (0.5f * sigmoid_f(raw) / (kCB * kCB * ls));
   }
   hyp[F] = 0.5f * inv_tot * inv_n * red[2] * sigmoid_f(__ldg(th + g.off_noise));
-  hyp[F + 1] = g.has_oscale ? 0.5f * inv_tot * inv_n * red[1] * sigmoid_f(__ldg(th + g.off_oscale)) : 0.0f;
+  // output scale: sum_ab (beta_a alphahat_b - Khat^-1_ab) k_ab with k = (Khat - (1 - rho) I) / rho collapses to
+  // (quad - n - (1 - rho) Str) / rho  (tr(Khat^-1 Khat) = n, beta . Khat alphahat = quad): no element-wise cancellation
+  const float Skt = (quad - n - (1.0f - mt.rho) * red[2]) / mt.rho;
+  hyp[F + 1] = g.has_oscale ? 0.5f * inv_tot * inv_n * Skt * sigmoid_f(__ldg(th + g.off_oscale)) : 0.0f;
   hyp[F + 2] = red[3] * inv_n;
 }
 
@@ -833,7 +1011,7 @@ bool make_map(CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint6
 
 struct BigLayout {
   int nb, npad, batch;                 // tiles per side, padded size, matrices per pass
-  size_t off_L, off_SB, off_u, off_r, off_v, off_a, off_ldet, off_part, off_mat, off_list, total;   // bytes
+  size_t off_L, off_SB, off_u, off_r, off_v, off_a, off_w, off_rowp, off_colp, off_ldet, off_part, off_mat, off_list, total;   // bytes
 };
 
 size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -842,7 +1020,7 @@ BigLayout big_layout(int n, long long matrices) {
   BigLayout L;
   L.nb = (n + NB - 1) / NB;
   L.npad = L.nb * NB;
-  const size_t per = (size_t)L.npad * L.npad * 4 + (size_t)L.nb * 2 * NB * NB * 4 + (size_t)L.npad * 32;
+  const size_t per = (size_t)L.npad * L.npad * 4 + (size_t)L.nb * 2 * NB * NB * 4 + (size_t)L.npad * 72 + (size_t)(L.nb * (L.nb - 1) / 2) * NB * 16;
   const size_t budget = (size_t)24 << 30;
   long long batch = std::max<long long>(1, std::min<long long>(matrices, (long long)(budget / per)));
   L.batch = (int)batch;
@@ -854,8 +1032,11 @@ BigLayout big_layout(int n, long long matrices) {
   L.off_r = take((size_t)L.batch * L.npad * 4);
   L.off_v = take((size_t)L.batch * L.npad * 4);
   L.off_a = take((size_t)L.batch * L.npad * 4);
+  L.off_w = take((size_t)L.batch * L.npad * 4);
+  L.off_rowp = take((size_t)L.batch * L.npad * 32);
+  L.off_colp = take((size_t)L.batch * (L.nb * (L.nb - 1) / 2) * NB * 16);
   L.off_ldet = take((size_t)L.batch * L.nb * 4);
-  L.off_part = take((size_t)L.batch * L.nb * 8 * 4);
+  L.off_part = take((size_t)L.batch * L.nb * 12 * 4);
   L.off_mat = take((size_t)L.batch * sizeof(BigMat));
   L.off_list = take((size_t)(L.batch + 1) * 3 * 4);      // three retry lists + their counters
   L.total = off;
@@ -909,13 +1090,20 @@ int launch_gp_mll_big(const GpArgs& g, void* ws, size_t ws_bytes, cudaStream_t s
   a.nb_max = L.nb; a.npad = L.npad;
   a.Lbuf = (float*)(base + L.off_L); a.SB = (float*)(base + L.off_SB);
   a.ubuf = (float4*)(base + L.off_u); a.rbuf = (float*)(base + L.off_r);
-  a.vbuf = (float*)(base + L.off_v); a.abuf = (float*)(base + L.off_a);
+  a.vbuf = (float*)(base + L.off_v); a.abuf = (float*)(base + L.off_a); a.wbuf = (float*)(base + L.off_w);
   a.ldet = (float*)(base + L.off_ldet); a.part = (float*)(base + L.off_part);
+  a.rowpart = (float*)(base + L.off_rowp); a.colpart = (float*)(base + L.off_colp); a.npairs = L.nb * (L.nb - 1) / 2;
   a.mat = (BigMat*)(base + L.off_mat);
   int* lists = (int*)(base + L.off_list);
   a.g = g;
   CUtensorMap mL, mS;
   int rc;
+  // PACOH_BIG_TIMING=1: per-phase device times of every pass on stderr (diagnostics; synchronises the stream)
+  static int timing = -1;
+  if (timing < 0) { const char* e = getenv("PACOH_BIG_TIMING"); timing = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  cudaEvent_t ev[6];
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  auto mark = [&](int i) { if (timing) cudaEventRecord(ev[i], st); };
   for (long long b0 = 0; b0 < matrices; b0 += L.batch) {
     a.B = (int)std::min<long long>(L.batch, matrices - b0);
     a.list = nullptr; a.count = nullptr;
@@ -924,6 +1112,7 @@ int launch_gp_mll_big(const GpArgs& g, void* ws, size_t ws_bytes, cudaStream_t s
       set_error("large-n GP path: cuTensorMapEncodeTiled failed");
       return PACOH_ERR_CUDA;
     }
+    mark(0);
     PACOH_CUDA_CHECK(cudaMemsetAsync(lists, 0, (size_t)(L.batch + 1) * 3 * 4, st));
     big_prep_kernel<<<a.B, 128, 0, st>>>(a, (int)b0);
     PACOH_CUDA_CHECK(cudaGetLastError());
@@ -948,13 +1137,30 @@ int launch_gp_mll_big(const GpArgs& g, void* ws, size_t ws_bytes, cudaStream_t s
       PACOH_CUDA_CHECK(cudaGetLastError());
     }
     a.list = nullptr; a.count = nullptr;
+    mark(1);
     for (int s = 1; s < L.nb; ++s)
       if ((rc = launch_big<M_UINV>(mL, mS, a, s, L.nb - s, st)) != PACOH_OK) return rc;
-    big_alpha_kernel<<<a.B * L.nb, 256, 0, st>>>(a);
+    mark(2);
+    big_ux_kernel<<<a.B * L.nb, 256, 0, st>>>(a, a.vbuf, a.abuf, 0);                 // alphahat = U v
+    big_resid_kernel<<<a.B * L.nb, NB, 0, st>>>(a, a.vbuf);                          // r' = r - Khat alphahat   (v is dead)
+    big_utx_kernel<<<a.B * L.nb, NB, 0, st>>>(a, a.vbuf, a.wbuf);                     // w = L^-1 r'
+    big_ux_kernel<<<a.B * L.nb, 256, 0, st>>>(a, a.wbuf, a.abuf, 1);                 // alphahat += U w
     PACOH_CUDA_CHECK(cudaGetLastError());
+    mark(3);
     if ((rc = launch_big<M_GRAD>(mL, mS, a, 0, L.nb, st)) != PACOH_OK) return rc;
+    mark(4);
+    big_gradfin_kernel<<<a.B * L.nb, NB, 0, st>>>(a);
+    big_dfeat_kernel<<<a.B * L.nb, NB, 0, st>>>(a);
     big_finish_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a);
     PACOH_CUDA_CHECK(cudaGetLastError());
+    mark(5);
+    if (timing) {
+      cudaEventSynchronize(ev[5]);
+      float ms[5];
+      for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+      fprintf(stderr, "[pacoh big] n=%d matrices=%d: cholesky %.3f ms, U=L^-T %.3f, alpha+refine %.3f, K^-1+grad %.3f, finish %.3f\n",
+              g.n, a.B, ms[0], ms[1], ms[2], ms[3], ms[4]);
+    }
   }
   return PACOH_OK;
 }

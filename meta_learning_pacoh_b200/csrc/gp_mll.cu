@@ -402,6 +402,18 @@ __global__ void __launch_bounds__(kGpWarps * 32, PACOH_GP_MINB(NC)) gp_mll_kerne
 
   // ---- write-out.  G = g' / (2 tot);  W = rho/2 g' k;  all gradients are of mll = L / n.
   //      sum_ab w_ab du_ab^2 = 2 sum_a u_a S1_a   (w symmetric, du antisymmetric) gives the lengthscale gradient.
+  // The stationary kernel is invariant to a common shift of the features: sum_a S1_a = 0 exactly.  Rounding leaves a
+  // residue (w is not bit-symmetric); removing its mean projects the gradient back onto that invariance, so that the
+  // kernel net's output-bias gradient (= sum over the points) cancels as far as the later fp32 sums allow.
+#pragma unroll
+  for (int f = 0; f < FT; ++f) {
+    float t = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) t += (lane + 32 * s < n) ? S1[s][f] : 0.0f;
+    t = warp_sum(t) * inv_n;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) S1[s][f] -= t;
+  }
   float S2[FT];
 #pragma unroll
   for (int f = 0; f < FT; ++f) S2[f] = 0.0f;

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(kGT, (MT == 2 ? PACOH_GPTC_MINB : 4)) gp_tc_ke
   __shared__ __align__(16) float s_feat[MT][kRows][RS];
   __shared__ float s_red[MT][WPM][8];                                        // [matrix][warp-in-matrix][slot]
   __shared__ float s_hyp[MT][8][2];                                           // hyper-parameters, one per designated thread
+  __shared__ float s_proj[MT][WPM][4];                                        // per-warp sums of S1 (shift-invariance projection)
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_s;
 
@@ -360,11 +361,24 @@ __global__ void __launch_bounds__(kGT, (MT == 2 ? PACOH_GPTC_MINB : 4)) gp_tc_ke
   red[3] = warp_sum(valid ? beta : 0.0f);
 #pragma unroll
   for (int f = 0; f < FT; ++f) red[4 + f] = warp_sum(valid ? 2.0f * (u[f] - sf[0][f]) * S1[f] : 0.0f);
+  // sum_a S1_a = 0 exactly (the kernel is invariant to a common feature shift); its rounding residue is removed below
+  float prj[FT];
+#pragma unroll
+  for (int f = 0; f < FT; ++f) prj[f] = warp_sum(valid ? S1[f] : 0.0f);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 4 + FT; ++i) s_red[mtx][wim][i] = red[i];
+#pragma unroll
+    for (int f = 0; f < FT; ++f) s_proj[mtx][wim][f] = prj[f];
   }
   __syncthreads();
+#pragma unroll
+  for (int f = 0; f < FT; ++f) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < WPM; ++w) t += s_proj[mtx][w][f];
+    S1[f] -= t * inv_n;
+  }
 
   if (pvalid) {
     float* hyp = a.dhyp + ((size_t)p * a.T + t) * gp_hyp_stride(F);

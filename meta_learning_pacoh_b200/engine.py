@@ -202,6 +202,53 @@ class MetaMLLEngine:
         return mll, packed, info
 
 
+class PinnedRing:
+    """Host->device upload of small per-step arrays (the sampled task indices) without a host synchronisation and
+    without the reuse race of a single pinned buffer: a ring of pinned staging buffers, each guarded by a CUDA event
+    recorded after its copy.  A slot is only rewritten once its previous copy has executed (event.synchronize() is a no-op
+    unless the host has run more than `slots` steps ahead of the device)."""
+
+    def __init__(self, device, slots=8, dtype=torch.int32):
+        self.device, self.dtype, self.slots = torch.device(device), dtype, slots
+        self._buf = [None] * slots
+        self._ev = [None] * slots
+        self._next = 0
+
+    def upload(self, array):
+        src = torch.from_numpy(np.ascontiguousarray(array))
+        assert src.dtype == self.dtype
+        k = self._next
+        self._next = (k + 1) % self.slots
+        if self._ev[k] is not None:
+            self._ev[k].synchronize()
+        if self._buf[k] is None or self._buf[k].numel() < src.numel():
+            self._buf[k] = torch.empty(max(src.numel(), 16), dtype=self.dtype).pin_memory()
+            self._ev[k] = torch.cuda.Event()
+        self._buf[k][:src.numel()].copy_(src)
+        out = self._buf[k][:src.numel()].to(self.device, non_blocking=True)
+        self._ev[k].record(torch.cuda.current_stream(self.device))
+        return out
+
+
+class FailureFlag:
+    """Sticky device-side record of the worst per-matrix status seen since the last check (no host synchronisation per
+    step).  The reference raises NotPSDError the moment a Cholesky fails (gpytorch psd_safe_cholesky); here the failing
+    matrices write mll = NaN / zero gradients and the exception is raised at the next ``check()`` -- every log period, at
+    the end of meta_fit and before any prediction."""
+
+    def __init__(self, device):
+        self.worst = torch.zeros((), dtype=torch.int32, device=device)
+
+    def update(self, info):
+        if info is not None:
+            torch.minimum(self.worst, info.min(), out=self.worst)
+
+    def check(self):
+        if int(self.worst.item()) < 0:
+            self.worst.zero_()
+            raise NotPSDError("a task kernel matrix was not positive definite after jitter 1e-4 since the last check")
+
+
 def check_info(info):
     """Host check of the per-matrix status (one device->host read): raises NotPSDError like the reference would."""
     if info is not None and int(info.min().item()) < 0:

@@ -66,6 +66,8 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         X, Y = self._build_task_dicts(meta_train_data)
         self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
         self._setup_optimizer(optimizer, lr_params, lr_decay)
+        self._idx_ring = eng.PinnedRing(self.device)
+        self._failures = eng.FailureFlag(self.device)
         self.fitted = False
 
     # ------------------------------------------------------------------ flat-layout packing
@@ -105,7 +107,9 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         """Meta-learns the GP prior parameters -- GPR_meta_mll.py:82-147."""
         assert (valid_tuples is None) or (all([len(valid_tuple) == 4 for valid_tuple in valid_tuples]))
         loss = torch.zeros((), device=self.device)
-        if self.learning_mode != 'vanilla':
+        # the reference gates on len(self.shared_parameters) > 0, which always holds (the likelihood's noise is always a
+        # shared parameter, GPR_meta_mll.py:56): 'vanilla' mode still trains the noise
+        if len(self.shared_parameters) > 0:
             t = time.time()
             cum_loss = torch.zeros((), device=self.device)
             if n_iter is None:
@@ -118,7 +122,7 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
                 self.lr_scheduler.step()
                 cum_loss = cum_loss + loss
                 if itr == 1 or itr % log_period == 0:
-                    eng.check_info(self._last_info)
+                    self._failures.check()
                     duration = time.time() - t
                     avg_loss = cum_loss / (log_period if itr > 1 else 1.0)
                     cum_loss = torch.zeros((), device=self.device)
@@ -131,16 +135,18 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
                         self.logger.info(message)
         else:
             self.logger.info('Vanilla mode - nothing to fit')
+        self._failures.check()
         self.fitted = True
         return loss.item()
 
     def _loss_and_grad(self, task_idx):
-        idx = torch.as_tensor(np.asarray(task_idx, dtype=np.int32)).to(self.device)
+        idx = self._idx_ring.upload(np.asarray(task_idx, dtype=np.int32))
         theta = self._pack()
         _, packed, info = self.engine.mll_fwd_bwd(theta, idx, want_mll=False, want_info=True)
         D = self.arch.D
         self._scatter_grad(-packed[:D])                 # loss = - sum_t mll_t
         self._last_info = info
+        self._failures.update(info)
         return -packed[D]
 
     # ------------------------------------------------------------------ prediction

@@ -51,7 +51,8 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
 
         X, Y = self._build_task_dicts(meta_train_data)
         self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
-        self._idx_host = torch.empty(self.task_batch_size, dtype=torch.int32).pin_memory()
+        self._idx_ring = eng.PinnedRing(self.device)
+        self._failures = eng.FailureFlag(self.device)
         self._group, self._peer = None, None
         self._rank, self._world = 0, 1
         self.fitted = False
@@ -92,7 +93,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             self.svgd_step(task_idx)
             self.lr_scheduler.step()
             if itr == 1 or itr % log_period == 0:
-                eng.check_info(self._last_info)
+                self._failures.check()
                 duration = time.time() - t
                 t = time.time()
                 message = 'Iter %d/%d - Time %.2f sec' % (itr, self.num_iter_fit, duration)
@@ -101,6 +102,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
                     message += ' - Valid-LL: %.3f - Valid-RMSE: %.3f - Calib-Err %.3f' % (valid_ll, valid_rmse, calibr_err)
                 if verbose:
                     self.logger.info(message)
+        self._failures.check()
         self.fitted = True
 
     def svgd_step(self, task_idx):
@@ -108,11 +110,9 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         ``task_idx``: numpy / sequence of task indices into the meta-training set (with repetitions)."""
         idx = np.asarray(task_idx, dtype=np.int32)
         T = idx.shape[0]
+        assert T >= self._world, "task batch (%d) smaller than the number of ranks (%d): every rank needs a task" % (T, self._world)
         lo, hi = eng.shard_bounds(T, self._rank, self._world)
-        if self._idx_host.numel() < hi - lo:
-            self._idx_host = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
-        self._idx_host[:hi - lo].copy_(torch.from_numpy(idx[lo:hi]))
-        idx_dev = self._idx_host[:hi - lo].to(self.device, non_blocking=True)
+        idx_dev = self._idx_ring.upload(idx[lo:hi])
         pre = eng.pre_factor(self.task_sizes[idx])                     # GLOBAL batch, harmonic mean of its n_t (random_gp.py:209-212)
         self._phi.prepare(self.particles)                              # K(theta) on a side stream, under the MLL kernels
         logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
@@ -125,6 +125,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             self.particles.grad = -phi
             self.optimizer.step()
         self._last_info, self._last_logp = info, logp
+        self._failures.update(info)
         return logp
 
     def svgd_step_host(self, x_batch, y_batch, global_tasks=None, wait=True):
@@ -184,6 +185,7 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             self.particles.grad = -phi
             self.optimizer.step()
         self._last_info = info
+        self._failures.update(info)
         out, ev = self._logp_host[slot], self._logp_event[slot]
         out.copy_(logp, non_blocking=True)
         ev.record(torch.cuda.current_stream(self.device))

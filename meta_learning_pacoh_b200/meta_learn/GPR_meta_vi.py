@@ -95,6 +95,8 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
         self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
         self._group, self._rank, self._world = None, 0, 1
         self._last_info = None
+        self._idx_ring = eng.PinnedRing(self.device)
+        self._failures = eng.FailureFlag(self.device)
         self.fitted = False
 
     def shard_tasks(self, group=None):
@@ -120,7 +122,7 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
             self.optimizer.step()
             self.lr_scheduler.step()
             if itr == 1 or itr % log_period == 0:
-                eng.check_info(self._last_info)
+                self._failures.check()
                 duration = time.time() - t
                 t = time.time()
                 message = 'Iter %d/%d - Loss: %.6f - Time %.2f sec' % (itr, self.num_iter_fit, loss.item(), duration)
@@ -129,14 +131,16 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
                     message += ' - Valid-LL: %.3f - Valid-RMSE: %.3f - Calib-Err %.3f' % (valid_ll, valid_rmse, calibr_err)
                 if verbose:
                     self.logger.info(message)
+        self._failures.check()
         self.fitted = True
         return loss.item()
 
     def _shard(self, task_idx):
         idx = np.asarray(task_idx, dtype=np.int32)
         T = idx.shape[0]
+        assert T >= self._world, "task batch (%d) smaller than the number of ranks (%d): every rank needs a task" % (T, self._world)
         lo, hi = eng.shard_bounds(T, self._rank, self._world)
-        return torch.from_numpy(idx[lo:hi].copy()).to(self.device), eng.pre_factor(self.task_sizes[idx])
+        return self._idx_ring.upload(idx[lo:hi]), eng.pre_factor(self.task_sizes[idx])
 
     def get_neg_elbo(self, task_idx, eps=None):
         """-mean_s [ log p(theta_s | data) - prior_factor * log q(theta_s) ] and its gradient w.r.t. the posterior
@@ -165,6 +169,7 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
             loss.backward()
             loss = loss.detach()
         self._last_info = info
+        self._failures.update(info)
         return loss
 
     # ------------------------------------------------------------------ prediction

@@ -162,5 +162,96 @@ def main():
         run_case(260, P=2, T=3, kw=dict(input_dim=3, mean_layers=(32, 32), kernel_layers=(32, 32), feature_dim=4))
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config #5 shapes: PACOH-MAP (outputscale, noise floor 1e-3), torch nn.Linear default init, raw hypers 0.
+def map_theta(lay, seed=30):
+    g = torch.Generator().manual_seed(seed)
+    th = torch.zeros(1, lay.D)
+    for name, (a, b) in lay.entries.items():
+        if "weight" in name or "bias" in name:
+            # fan-in of the layer: weight (out, in) -> in; bias uses the same bound (torch.nn.Linear.reset_parameters)
+            pref = name.rsplit(".", 1)[0]
+            wa, wb = lay.entries[pref + ".weight"]
+            ba, bb = lay.entries[pref + ".bias"]
+            fan_in = (wb - wa) // (bb - ba)
+            bound = 1.0 / np.sqrt(fan_in)
+            th[0, a:b] = (torch.rand(b - a, generator=g) * 2 - 1) * bound
+    return th.numpy()
+
+
+def config5(n, T=4, T_time=0, fp32_ref=True):
+    kw = dict(input_dim=1, outputscale=True, noise_floor=1e-3)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    train = orc.sinusoid_tasks(max(T, 4), n, seed=26)
+    stats = orc.normalization_stats(train)
+    tasks64 = [orc.prepare_task(xx, yy, stats, torch.float64) for xx, yy in train]
+    x = np.stack([t[0].numpy() for t in tasks64]).astype(np.float32)
+    y = np.stack([t[1].numpy() for t in tasks64]).astype(np.float32)
+    theta = map_theta(lay)
+    idx = list(range(T))
+    e = eng.MetaMLLEngine(arch, x, y, dev)
+    th = torch.from_numpy(theta).to(dev)
+    tidx = torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(dev)
+    mll, packed, info = e.mll_fwd_bwd(th, tidx)
+    torch.cuda.synchronize()
+    tasks = [(torch.from_numpy(x[i]).double(), torch.from_numpy(y[i]).double()) for i in idx]
+    mu, sigma = orc.hyper_prior_params(lay, 0.5, 3.0, torch.float64)
+    t0 = time.time()
+    logp64, g64, mll64 = orc.meta_log_prob_and_grad(torch.from_numpy(theta).double(), lay, tasks, 0.0, mu, sigma)
+    t_or = time.time() - t0
+    g64 = g64.numpy() / eng.pre_factor([n] * T)        # d sum_t mll / d theta
+    g = packed[:lay.D].cpu().numpy()[None, :]
+    print("== config5 n=%d T=%d: info[min,max]=%d,%d  mll rel err %.3e  (oracle fp64 %.1f s)" %
+          (n, T, int(info.min()), int(info.max()), rel(mll.cpu().numpy(), mll64.numpy()), t_or))
+    scale = np.abs(g64).max()
+    worst = 0.0
+    for nm, (a, b) in arch.entries().items():
+        err = np.abs(g[:, a:b] - g64[:, a:b]).max() / max(np.abs(g64[:, a:b]).max(), 1e-3 * scale)
+        worst = max(worst, err)
+        print("      %-24s grp-rel %.3e   |ref|max %.3e" % (nm, err, np.abs(g64[:, a:b]).max()))
+    print("   WORST group error %.3e  %s" % (worst, "OK" if worst <= 1e-4 else "** ABOVE 1e-4 **"))
+    if fp32_ref:
+        tasks32 = [(a.float(), b.float()) for a, b in tasks]
+        mu32, s32 = orc.hyper_prior_params(lay, 0.5, 3.0, torch.float32)
+        _, g32, mll32 = orc.meta_log_prob_and_grad(torch.from_numpy(theta).float(), lay, tasks32, 0.0, mu32, s32)
+        g32 = g32.numpy() / eng.pre_factor([n] * T)
+        w32 = max(np.abs(g32[:, a:b] - g64[:, a:b]).max() / max(np.abs(g64[:, a:b]).max(), 1e-3 * scale) for a, b in arch.entries().values())
+        print("   fp32 torch oracle (the reference's own precision) vs fp64: mll %.3e  worst group %.3e" % (rel(mll32.numpy(), mll64.numpy()), w32))
+    if T_time:
+        train = orc.sinusoid_tasks(T_time, n, seed=27)
+        xs = np.stack([orc.prepare_task(xx, yy, stats, torch.float32)[0].numpy() for xx, yy in train])
+        ys = np.stack([orc.prepare_task(xx, yy, stats, torch.float32)[1].numpy() for xx, yy in train])
+        e2 = eng.MetaMLLEngine(arch, xs, ys, dev)
+        tidx2 = torch.arange(T_time, dtype=torch.int32, device=dev)
+        e2.mll_fwd_bwd(th, tidx2)
+        torch.cuda.synchronize()
+        with eng.StageTiming() as stg:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            reps = 3
+            for _ in range(reps):
+                _, _, inf2 = e2.mll_fwd_bwd(th, tidx2)
+            ev1.record()
+            ev1.synchronize()
+            ms, calls = stg.read()
+        tot = ev0.elapsed_time(ev1) / reps
+        flop = T_time * (n ** 3 + 2.0 * n * n)
+        print("   timing n=%d T=%d: %.2f ms per fwd+bwd (stages per call: %s)  GP stage %.1f TFLOP/s (n^3 + 2 n^2)  info max %d" %
+              (n, T_time, tot, {k: round(v / max(calls, 1), 3) for k, v in ms.items()}, flop / (ms["gp_mll"] / max(calls, 1) * 1e-3) / 1e12,
+               int(inf2.max())))
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "config5":
+    for n, tt in ((512, 1024), (1024, 1024), (2048, 1024)):
+        try:
+            config5(n, T=3, T_time=tt)
+        except Exception as ex:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+    sys.exit(0)
+
+
 if __name__ == "__main__":
     main()

@@ -60,23 +60,35 @@ def oracle64(lay, x, y, theta, idx, prior_factor=0.01, wstd=0.5, bstd=3.0):
     return mll.numpy(), logp.numpy(), g.numpy()
 
 
-# Extended range 64 < n <= 128 (no BASELINE config lives there): the in-place Gauss-Jordan sweep over twice as many pivots
-# is measurably less accurate than a Cholesky solve on ill-conditioned Gram matrices -- worst per-group gradient error
-# against fp64 over random prior particles (tests/manual/gp_accuracy_vs_n.py): 2e-5 .. 7e-5 for n = 65 .. 112 and 4e-4
-# for one n = 128 case, where the fp32 oracle (the reference's own precision) sits at 1e-5 .. 5e-5.  Values (mll, logp)
-# hold the 1e-4 bar everywhere; gradients for n > 64 are tested at 5e-4.
-RTOL_N128 = 5e-4
+# n > 64 runs the blocked Cholesky path (csrc/gp_big.cu) and holds the same 1e-4 bar as the small-matrix kernels (round 1
+# tested 64 < n <= 128 at 5e-4 on an in-place Gauss-Jordan sweep; that kernel is now only reachable with PACOH_GP=tc128).
+RTOL_N128 = RTOL
+def assert_groups(arch, got, want, tol=RTOL, ref32=None):
+    """Per parameter group, error in the group's max-norm, relative to max(|group|, 1e-3 * overall gradient scale).
 
-
-def assert_groups(arch, got, want, tol=RTOL):
-    """per parameter group, error in the group's max-norm; groups whose true gradient is (numerically) zero -- the kernel
-    net's output bias, to which the stationary SE kernel is invariant, only sees the tiny prior term -- are measured
-    against 1% of the overall gradient scale instead."""
+    A group whose true gradient is numerically zero has no meaningful relative error of its own: the kernel net's output
+    bias (the stationary SE kernel is invariant to a feature shift, so its likelihood gradient is an exact cancellation of
+    O(scale) terms and only the tiny prior term survives).  What fp32 leaves there is summation residue -- the reference's
+    own fp32 torch path included: on test_every_matrix_size_up_to_128[65] the fp32 oracle is off by 3.2e-6 (2.3e-4 of the
+    floor) where this engine is off by 1.9e-6.  For such degenerate groups (below 1% of the scale) the bound is therefore
+    the larger of the 1e-4 floor bound and 1.5 x the fp32 oracle's own error, when the caller supplies it (``ref32``)."""
     scale = np.abs(want).max()
     for name, (a, b) in arch.entries().items():
         ref = want[:, a:b]
         err = np.abs(got[:, a:b] - ref).max()
-        assert err <= tol * max(np.abs(ref).max(), 1e-2 * scale), (name, err, np.abs(ref).max())
+        gmax = np.abs(ref).max()
+        bound = tol * max(gmax, 1e-3 * scale)
+        if ref32 is not None and gmax < 1e-2 * scale:
+            bound = max(bound, 1.5 * np.abs(ref32[:, a:b] - ref).max())
+        assert err <= bound, (name, err, gmax, scale)
+
+
+def oracle32(lay, x, y, theta, idx, prior_factor=0.01, wstd=0.5, bstd=3.0):
+    """The same oracle in fp32: the precision the reference's own torch path runs in."""
+    tasks = [(torch.from_numpy(np.asarray(x[i])).float(), torch.from_numpy(np.asarray(y[i])).float()) for i in range(len(x))]
+    mu, sigma = orc.hyper_prior_params(lay, wstd, bstd, torch.float32)
+    _, g, _ = orc.meta_log_prob_and_grad(torch.as_tensor(theta).float(), lay, [tasks[i] for i in idx], prior_factor, mu, sigma)
+    return g.double().numpy()
 
 
 # ------------------------------------------------------------------------------------------ golden vectors
@@ -168,7 +180,8 @@ def _prior_particles(lay, P, seed):
                                65, 72, 80, 97, 100, 112, 127, 128])
 def test_every_matrix_size_up_to_128(eng, n):
     """all NC instantiations of the warp-per-matrix kernel (n <= 32), the tensor-memory kernel with two matrices per CTA
-    (n <= 64) and with one (n <= 128), ragged last tile of the MLP kernels, repeated tasks."""
+    (n <= 64), the blocked Cholesky path with a single tile (64 < n <= 128), ragged last tile of the MLP kernels,
+    repeated tasks."""
     x, y = _synthetic(5, n, seed=n)
     lay, arch = orc.Layout(1), eng.GPArch(1)
     theta = _prior_particles(lay, 3, 100 + n)
@@ -177,7 +190,7 @@ def test_every_matrix_size_up_to_128(eng, n):
     mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
     assert (info == 0).all()
     assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
-    assert_groups(arch, score, g64, tol=RTOL if n <= 64 else RTOL_N128)
+    assert_groups(arch, score, g64, ref32=oracle32(lay, x, y, theta, idx))
 
 
 @pytest.mark.parametrize("kw", [
@@ -235,7 +248,9 @@ def test_tensor_core_gp_kernel_shapes(eng, n, kw):
     (64, 1, dict(input_dim=2, mean_kind="zero", covar_kind="NN")),                          # both kernels' size range in one batch
     (40, 7, dict(input_dim=3, mean_kind="constant", covar_kind="SE")),
     (57, 20, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),                        # PACOH-MAP variant
-    (100, 40, dict(input_dim=1)),                                                          # one matrix per CTA
+    (100, 40, dict(input_dim=1)),                                                          # small kernels' sizes inside a large-n batch
+    (300, 60, dict(input_dim=1)),                                                          # blocked path: 1 .. 3 tiles per matrix in one batch
+    (260, 129, dict(input_dim=2, mean_kind="constant", covar_kind="SE")),
 ])
 def test_ragged_task_sets_match_oracle(eng, n_max, lo, kw):
     """Tasks with different numbers of points (the reference's per-task loop handles them implicitly, random_gp.py:214-217;
@@ -295,10 +310,10 @@ def test_map_demo_first_iteration_matches_logged_loss(eng, golden_dir):
     a, b = lay.entries["noise_raw"]; g_ref[a:b] = m.raw_noise.grad
     a, b = lay.entries["outputscale_raw"]; g_ref[a:b] = m.raw_outputscale.grad.reshape(1)
     got = -packed[:lay.D].cpu().numpy().reshape(1, -1)
-    assert_groups(arch, got, g_ref.numpy().reshape(1, -1), tol=2e-4)
+    assert_groups(arch, got, g_ref.numpy().reshape(1, -1))
 
 
-@pytest.mark.parametrize("n", [8, 40, 96])  # register kernel / tensor-memory kernel (two matrices per CTA retry together) / one per CTA
+@pytest.mark.parametrize("n", [8, 40, 96, 200])  # register kernel / tensor-memory kernel (two matrices per CTA retry together) / blocked path (retry list)
 def test_jitter_ladder_and_not_psd_reporting(eng, n):
     """duplicate inputs + vanishing noise: singular K.  The kernel must climb the 1e-6/1e-5/1e-4 jitter ladder
     (gpytorch psd_safe_cholesky) or report failure; the host wrapper raises NotPSDError on failure."""
@@ -326,13 +341,91 @@ def test_jitter_ladder_and_not_psd_reporting(eng, n):
     assert torch.equal(packed1[:D], packed[D:2 * D])
 
 
+@pytest.mark.parametrize("n,P,T,kw", [
+    (129, 2, 3, dict(input_dim=1)),                                                            # two tiles, the second almost empty
+    (200, 2, 4, dict(input_dim=1)),
+    (256, 1, 3, dict(input_dim=1, outputscale=True, noise_floor=1e-3)),                        # exactly two full tiles
+    (300, 2, 3, dict(input_dim=3, mean_layers=(32, 32), kernel_layers=(32, 32), feature_dim=4)),
+    (385, 1, 2, dict(input_dim=2, mean_kind="constant", covar_kind="SE")),
+    (512, 2, 2, dict(input_dim=1)),
+])
+def test_blocked_cholesky_path_matches_oracle(eng, n, P, T, kw):
+    """csrc/gp_big.cu (n > 64): left-looking blocked Cholesky, U = L^-T, Khat^-1 tiles on tcgen05 (3xTF32), prior particles."""
+    x, y = _synthetic(4, n, d=kw["input_dim"], seed=n)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    theta = _prior_particles(lay, P, 300 + n)
+    idx = [3, 0, 0, 2][:T]
+    mll, logp, score, info = run_engine(eng, arch, x, y, theta, idx)
+    mll64, logp64, g64 = oracle64(lay, x, y, theta, idx)
+    assert (info == 0).all()
+    assert relmax(mll, mll64) <= RTOL and relmax(logp, logp64) <= RTOL
+    assert_groups(arch, score, g64, ref32=oracle32(lay, x, y, theta, idx))
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048])
+def test_config5_sizes_match_fp64_oracle(eng, n):
+    """BASELINE config #5 (PACOH-MAP, 512 - 2048 points per task: GPR_meta_mll.py:104-119 with dense Cholesky forced):
+    sinusoid tasks, torch.nn.Linear default initialisation, raw hyper-parameters 0, spot-check of 3 tasks against fp64."""
+    kw = dict(input_dim=1, outputscale=True, noise_floor=1e-3)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    train = orc.sinusoid_tasks(4, n, seed=26)
+    stats = orc.normalization_stats(train)
+    tasks = [orc.prepare_task(xx, yy, stats, torch.float64) for xx, yy in train]
+    x = np.stack([t[0].numpy() for t in tasks]).astype(np.float32)
+    y = np.stack([t[1].numpy() for t in tasks]).astype(np.float32)
+    theta = orc.MAPOracle(train, weight_decay=0.0, seed=30).flat_parameters(lay).numpy()
+    idx = [2, 0, 3]
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    mll, packed, info = e.mll_fwd_bwd(torch.from_numpy(theta).to(DEV), torch.tensor(idx, dtype=torch.int32, device=DEV))
+    mu, sigma = orc.hyper_prior_params(lay, 0.5, 3.0, torch.float64)
+    batch = [(torch.from_numpy(x[i]).double(), torch.from_numpy(y[i]).double()) for i in idx]
+    _, g64, mll64 = orc.meta_log_prob_and_grad(torch.from_numpy(theta).double(), lay, batch, 0.0, mu, sigma)
+    g64 = g64.numpy() / orc.pre_factor([n] * len(idx))                    # d sum_t mll_t / d theta
+    mu32, sigma32 = orc.hyper_prior_params(lay, 0.5, 3.0, torch.float32)
+    _, g32, _ = orc.meta_log_prob_and_grad(torch.from_numpy(theta).float(), lay, [(a.float(), b.float()) for a, b in batch], 0.0, mu32, sigma32)
+    g32 = g32.double().numpy() / orc.pre_factor([n] * len(idx))
+    assert (info.cpu().numpy() == 0).all()
+    assert relmax(mll.cpu().numpy(), mll64.numpy()) <= RTOL
+    assert abs(float(packed[-1]) - float(mll64.sum())) <= RTOL * abs(float(mll64.sum()))
+    assert_groups(arch, packed[:lay.D].cpu().numpy()[None, :], g64, ref32=g32)
+
+
+def test_config5_full_batch_properties(eng):
+    """1024 tasks x 1024 points (config #5's middle size) in one call: duplicates count twice, the batch sum is the sum of
+    the per-task values, repeated calls are bitwise identical."""
+    n, T = 1024, 1024
+    kw = dict(input_dim=1, outputscale=True, noise_floor=1e-3)
+    lay, arch = orc.Layout(**kw), eng.GPArch(**kw)
+    x, y = _synthetic(T, n, seed=5)
+    theta = torch.from_numpy(orc.MAPOracle(orc.sinusoid_tasks(2, 8, seed=26), weight_decay=0.0, seed=30).flat_parameters(lay).numpy()).to(DEV)
+    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    idx = torch.arange(T, dtype=torch.int32, device=DEV)
+    mll, packed, info = e.mll_fwd_bwd(theta, idx)
+    assert int(info.abs().max()) == 0 and bool(torch.isfinite(mll).all())
+    assert abs(float(packed[-1]) - float(mll.double().sum())) <= 1e-5 * abs(float(mll.double().sum()))
+    mll2, packed2, _ = e.mll_fwd_bwd(theta, idx)
+    assert torch.equal(packed, packed2) and torch.equal(mll, mll2)
+    sub = torch.tensor([5, 9, 9, 700], dtype=torch.int32, device=DEV)
+    mll_s, packed_s, _ = e.mll_fwd_bwd(theta, sub)
+    assert torch.equal(mll_s[0, 1], mll_s[0, 2])
+    assert relmax(mll_s.cpu().numpy()[0], mll.cpu().numpy()[0, [5, 9, 9, 700]]) <= 1e-6
+    one = [e.mll_fwd_bwd(theta, torch.tensor([i], dtype=torch.int32, device=DEV))[1][:lay.D].double() for i in (5, 9, 700)]
+    want = one[0] + 2 * one[1] + one[2]
+    assert float((packed_s[:lay.D].double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
 def test_unsupported_sizes_fail_loudly(eng):
     from meta_learning_pacoh_b200._lib import PacohError
     arch = eng.GPArch(1)
-    x, y = _synthetic(2, 130)
-    e = eng.MetaMLLEngine(arch, x, y, DEV)
+    x, y = _synthetic(2, 4100)
     with pytest.raises(PacohError):
+        e = eng.MetaMLLEngine(arch, x, y, DEV)
         e.mll_fwd_bwd(torch.zeros(2, arch.D, device=DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))
+    wide = eng.GPArch(6, mean_layers=(20, 12), kernel_layers=(40,), feature_dim=7)       # F > 4 has no large-n kernel
+    x, y = _synthetic(2, 130, d=6)
+    with pytest.raises(PacohError):
+        e = eng.MetaMLLEngine(wide, x, y, DEV)
+        e.mll_fwd_bwd(torch.zeros(2, wide.D, device=DEV), torch.tensor([0, 1], dtype=torch.int32, device=DEV))
     with pytest.raises(NotImplementedError):
         eng.SVGDDirection(4, 10, DEV, kernel="Matern")
 

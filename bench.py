@@ -1,15 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the PACOH meta-training hot path (BASELINE.json metric: task-particle MLL+grad evals/s).
 
-    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU under torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's loop structure on the host CPU (oracle port)
+    python bench.py [--config {1..5}] [--points N] --gpus N --steps K --warmup W      # this engine (torchrun for N > 1)
+    python bench.py --impl reference [--config ...] --gpus N --steps K --warmup W     # the reference's loop structure on the host CPU
 
-Workload (config.workload): BASELINE configs[3], the configuration the metric and the north-star target are quoted
-on -- PACOH-SVGD, 64 particles x 4096 synthetic sinusoid tasks x 50 points, (32,32) mean and kernel nets, F = 2; it fits
-one GPU.  One "step" = one full SVGD meta-training step on one sampled batch of T = 4096 tasks (with replacement):
-batched MLL forward+backward for all 64 x 4096 (particle, task) pairs, hyper-prior, SVGD direction with the median
-heuristic, Adam update.  For N > 1 the same global batch is task-sharded over the ranks (strong scaling) with one cross-rank
-all-reduce of the packed (P, D+1) gradient buffer per step.  One eval = one (particle, task) MLL value + its gradient.
+BASELINE configs (SURVEY 8 notation: P parameter vectors x T tasks per step x n points):
+  1  PACOH-MAP  GPRegressionMetaLearned, 20 sinusoid tasks x 5 points, task_batch_size 5 (demo.py)         P=1  T=5    n=5
+  2  PACOH-SVGD GPRegressionMetaLearnedSVGD, 10 particles, 20 tasks x 5 points                             P=10 T=20   n=5
+  3  PACOH-VI   GPRegressionMetaLearnedVI, 8 ELBO samples, 256 tasks x 20 points                           P=8  T=256  n=20
+  4  PACOH-SVGD 64 particles x 4096 tasks x 50 points   <- DEFAULT: the configuration the metric and target are quoted on
+  5  PACOH-MAP  1024 tasks x {512, 1024, 2048} points (--points, default 2048): the Cholesky-bound regime      P=1  T=1024
+
+One "step" = one iteration of the learner's meta_fit loop body on one freshly sampled batch (with replacement): batched MLL
+forward + backward for all P x T (particle, task) pairs, hyper-prior, SVGD direction / ELBO gradient, optimizer update.  One
+eval = one (particle, task) MLL value + its gradient.  For N > 1 the same global batch is task-sharded over the ranks
+(strong scaling) with one cross-rank sum of the packed gradient buffer per step.
 """
 import argparse
 import json
@@ -25,10 +30,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-P, T, N_PTS, D_IN, HID, FEAT = 64, 4096, 50, 1, (32, 32), 2
-CPU_SLICE_T = 64                      # tasks per CPU-baseline step (bounded sample of the same workload)
+D_IN, HID, FEAT = 1, (32, 32), 2
 METRIC = "task-particle MLL+grad evals/s"
 UNIT = "evals/s"
+
+CONFIGS = {
+    1: dict(kind="map", P=1, T_total=20, T=5, n=5, cpu_T=5, name="PACOH-MAP demo.py: 20 sinusoid tasks x 5 points, task_batch_size 5 (BASELINE configs[0])"),
+    2: dict(kind="svgd", P=10, T_total=20, T=20, n=5, cpu_T=20, name="PACOH-SVGD: 10 particles x 20 sinusoid tasks x 5 points (BASELINE configs[1])"),
+    3: dict(kind="vi", P=8, T_total=256, T=256, n=20, cpu_T=64, name="PACOH-VI: 8 ELBO samples x 256 sinusoid tasks x 20 points (BASELINE configs[2])"),
+    4: dict(kind="svgd", P=64, T_total=4096, T=4096, n=50, cpu_T=16, name="PACOH-SVGD meta-training step: 64 particles x 4096 sinusoid tasks x 50 points (BASELINE configs[3])"),
+    5: dict(kind="map", P=1, T_total=1024, T=1024, n=2048, cpu_T=2, name="PACOH-MAP large-context step: 1024 sinusoid tasks x %d points, dense Cholesky (BASELINE configs[4])"),
+}
+
+
+def get_config(args):
+    c = dict(CONFIGS[args.config])
+    if args.config == 5:
+        c["n"] = args.points
+        c["name"] = c["name"] % args.points
+    return c
 
 
 def mac(out_dim):
@@ -39,31 +59,31 @@ def mac(out_dim):
     return m + prev * out_dim
 
 
-def flops_per_eval(n=N_PTS, F=FEAT):
-    """F_eval(n) = 6n(MAC(1)+MAC(F)) + n^2(7F+6) + n^3 + 2n^2  (842.4 kFLOP at n=50)."""
-    return 6 * n * (mac(1) + mac(F)) + n * n * (7 * F + 6) + n ** 3 + 2 * n * n
+def kernel_flops(n, F=FEAT):
+    """algorithmic FLOPs per eval by kernel; F_eval(n) = 6n(MAC(1)+MAC(F)) + n^2(7F+6) + n^3 + 2n^2."""
+    return {"mlp_fwd": 2 * n * (mac(1) + mac(F)), "gp_mll": n * n * (7 * F + 6) + n ** 3 + 2 * n * n, "mlp_bwd": 4 * n * (mac(1) + mac(F))}
 
 
-KERNEL_FLOPS = {   # algorithmic FLOPs per eval attributed to each kernel (sums to flops_per_eval)
-    "mlp_fwd": lambda: 2 * N_PTS * (mac(1) + mac(FEAT)),
-    "gp_mll": lambda: N_PTS ** 2 * (7 * FEAT + 6) + N_PTS ** 3 + 2 * N_PTS ** 2,
-    "mlp_bwd": lambda: 4 * N_PTS * (mac(1) + mac(FEAT)),
-}
+def flops_per_eval(n, F=FEAT):
+    return sum(kernel_flops(n, F).values())
 
 
-def config_dict(n_gpus):
-    return {"workload": "PACOH-SVGD meta-training step: 64 particles x 4096 sinusoid tasks x 50 points "
-                        "(BASELINE configs[3]); mean/kernel MLP (32,32), F=2, D=2342; task batch sampled with replacement",
-            "particles": P, "tasks_per_step": T, "points_per_task": N_PTS, "evals_per_step": P * T,
-            "flops_per_eval": flops_per_eval(), "parallelism": "task-sharded x%d, 1 all-reduce/step" % n_gpus if n_gpus > 1 else "single GPU",
-            "l2": "per-step working set (intermediate mean/feature/gradient buffers) is ~0.33 GB per GPU at N=1, larger than "
-                  "the 126 MB L2; every step streams a freshly sampled batch (no flush needed)"}
+def config_dict(cfg, n_gpus, extra=None):
+    d = {"workload": cfg["name"] + "; mean/kernel MLP (32,32), F=2; task batch sampled with replacement", "config_id": cfg["id"],
+         "particles": cfg["P"], "tasks_per_step": cfg["T"], "points_per_task": cfg["n"], "evals_per_step": cfg["P"] * cfg["T"],
+         "flops_per_eval": flops_per_eval(cfg["n"]),
+         "parallelism": "task-sharded x%d, 1 cross-rank sum per step" % n_gpus if n_gpus > 1 else "single GPU",
+         "l2": "every step streams a freshly sampled batch; the per-step working set (intermediate mean / feature / gradient buffers, "
+               "and the factor tiles of config 5) exceeds the 126 MB L2 for configs 4 and 5; configs 1-3 are launch / latency bound "
+               "and live in L2 by nature (no flush: that is their steady state)"}
+    d.update(extra or {})
+    return d
 
 
-def make_data():
+def make_data(cfg):
     from meta_learning_pacoh_b200.data_sim import SinusoidDataset
     ds = SinusoidDataset(random_state=np.random.RandomState(26))
-    return ds.generate_meta_train_data(n_tasks=T, n_samples=N_PTS)
+    return ds.generate_meta_train_data(n_tasks=cfg["T_total"], n_samples=cfg["n"])
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -110,55 +130,126 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_reference_steps(steps, warmup, data):
-    """The reference's loop structure on the host CPU (oracle/pacoh_oracle.py::SVGDOracle: per-task Python loop with
-    P-batched torch ops, autograd score, SVGD phi, Adam -- random_gp.py:206-222, svgd.py:12-28), all host threads, on a
-    bounded sample of the workload: the same 64 particles and 50-point tasks, CPU_SLICE_T tasks per step."""
+def cpu_stepper(cfg, data, threads):
+    """The reference's loop structure on the host CPU (oracle/pacoh_oracle.py: per-task Python loop with P-batched torch ops,
+    autograd, SVGD phi / ELBO / MAP loss, Adam(W) -- random_gp.py:206-222, svgd.py:12-28, GPR_meta_vi.py:216-224,
+    GPR_meta_mll.py:104-117) on a bounded sample of the workload: the same particles and points per task, cfg['cpu_T'] tasks
+    per step.  Returns (step function, evals per step)."""
     import torch
     from oracle import pacoh_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    stats = orc.normalization_stats(data)
-    tasks = [orc.prepare_task(x, y, stats) for x, y in data[:CPU_SLICE_T]]
+    torch.set_num_threads(threads)
+    Tc, P = cfg["cpu_T"], cfg["P"]
+    sub = data[:max(Tc, 2)]
+    if cfg["kind"] == "map":
+        m = orc.MAPOracle(sub, weight_decay=0.0, seed=30, task_batch_size=Tc)
+        return (lambda: m.step()), Tc
+    stats = orc.normalization_stats(sub)
+    tasks = [orc.prepare_task(x, y, stats) for x, y in sub[:Tc]]
     lay = orc.Layout(D_IN)
     mu, sigma = orc.hyper_prior_params(lay, 0.5, 3.0)
     g = torch.Generator().manual_seed(30)
-    particles = mu + sigma * torch.randn(P, lay.D, generator=g)
-    s = orc.SVGDOracle(tasks, lay, particles, seed=30)
+    if cfg["kind"] == "svgd":
+        s = orc.SVGDOracle(tasks, lay, mu + sigma * torch.randn(P, lay.D, generator=g), seed=30)
+        return (lambda: s.step()), P * Tc
+    loc = (0.1 * torch.randn(lay.D, generator=g)).requires_grad_(True)
+    scale = (np.log(0.1) + 0.1 * torch.randn(lay.D, generator=g)).requires_grad_(True)
+    opt = torch.optim.Adam([loc, scale], lr=1e-3)
+
+    def vi_step():
+        eps = torch.randn(P, lay.D, generator=g)
+        opt.zero_grad()
+        _, dloc, dscale, _ = orc.vi_neg_elbo_and_grad(loc.detach(), scale.detach(), eps, lay, tasks, 0.01, mu, sigma)
+        loc.grad, scale.grad = dloc, dscale
+        opt.step()
+    return vi_step, P * Tc
+
+
+def cpu_protocol(cfg, data, reps=5, iters=10, warmup=1, threads=None):
+    """experiments/compuational_comparison.py:49-55: meta_fit(n_iter=10) timed `reps` times; mean / std of evals per second."""
+    threads = threads or (os.cpu_count() or 1)
+    step, evals = cpu_stepper(cfg, data, threads)
     for _ in range(warmup):
-        s.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        s.step()
-    dt = time.perf_counter() - t0
-    return P * CPU_SLICE_T * steps / dt, dt / steps, torch.get_num_threads()
+        step()
+    rates, secs = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            step()
+        dt = time.perf_counter() - t0
+        rates.append(evals * iters / dt)
+        secs.append(dt / iters)
+    return float(np.mean(rates)), float(np.std(rates)), float(np.mean(secs)), threads
+
+
+def cpu_baseline_dict(cfg, data, quick=False):
+    v, sd, sec, cores = cpu_protocol(cfg, data, reps=3 if quick else 5, iters=5 if quick else 10)
+    v1, sd1, sec1, _ = cpu_protocol(cfg, data, reps=2, iters=3 if quick else 5, threads=1)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "std": sd,
+            "sample": "%d-task slice of the %d-task batch per step (%d parameter vectors x %d points), %d x %d iterations "
+                      "(experiments/compuational_comparison.py:49-55 protocol), %.3f s/step" % (cfg["cpu_T"], cfg["T"], cfg["P"], cfg["n"],
+                                                                                             3 if quick else 5, 5 if quick else 10, sec),
+            "single_thread": {"value": v1, "std": sd1, "cores": 1, "s_per_step": sec1}}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    data = make_data()[:CPU_SLICE_T]
-    steps = max(1, args.steps)
-    warm = min(args.warmup, 2)
-    value, sec_per_step, cores = cpu_reference_steps(steps, warm, data)
-    sample = "%d-task slice of the 4096-task batch per step (64 particles x 50 points), %d steps" % (CPU_SLICE_T, steps)
+    cfg = get_config(args)
+    cfg["id"] = args.config
+    data = make_data(dict(cfg, T_total=max(cfg["cpu_T"], 2)))
+    steps, warm = max(1, args.steps), min(args.warmup, 2)
+    step, evals = cpu_stepper(cfg, data, os.cpu_count() or 1)
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    sec = (time.perf_counter() - t0) / steps
+    value = evals / sec
+    import torch
+    cores = torch.get_num_threads()
+    sample = "%d-task slice of the %d-task batch per step (%d parameter vectors x %d points), %d steps" % (cfg["cpu_T"], cfg["T"], cfg["P"], cfg["n"], steps)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(args.gpus),
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(cfg, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference loop structure (per-task Python loop, P-batched torch ops, autograd) restated in oracle/; "
-                    "gpytorch/pyro are not installable offline. ms_per_step is for the %d-task slice." % CPU_SLICE_T}
+                    "gpytorch/pyro are not installable offline. ms_per_step is for the %d-task slice; evals/s normalises it." % cfg["cpu_T"]}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ this engine
+def build_model(cfg, data):
+    from meta_learning_pacoh_b200.meta_learn import GPRegressionMetaLearned, GPRegressionMetaLearnedSVGD, GPRegressionMetaLearnedVI
+    if cfg["kind"] == "svgd":
+        return GPRegressionMetaLearnedSVGD(data, num_particles=cfg["P"], random_seed=30)
+    if cfg["kind"] == "vi":
+        return GPRegressionMetaLearnedVI(data, svi_batch_size=cfg["P"], random_seed=30)
+    return GPRegressionMetaLearned(data, task_batch_size=cfg["T"], random_seed=30)
+
+
+def count_kernels(fn):
+    """Number of GPU kernels one call of fn() launches (torch profiler / CUPTI), and how many of them are this library's."""
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in e.name.lower() and "memset" not in e.name.lower()]
+    own = [n for n in names if "pacoh" in n]
+    return len(names), len(own), sorted(set(n.split("(")[0][-60:] for n in own))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from meta_learning_pacoh_b200 import engine as eng
-    from meta_learning_pacoh_b200.meta_learn import GPRegressionMetaLearnedSVGD
 
+    cfg = get_config(args)
+    cfg["id"] = args.config
+    P, T, n = cfg["P"], cfg["T"], cfg["n"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,25 +259,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
 
-    data = make_data()
-    model = GPRegressionMetaLearnedSVGD(data, num_particles=P, random_seed=30)
+    data = make_data(cfg)
+    model = build_model(cfg, data)
     if world > 1:
         model.shard_tasks()
+    peer = getattr(model, "_peer", None)
     collective = ("none (single GPU)" if world == 1 else
-                  "all-reduce fused into the finalize kernel over NVLink peer memory (pacoh_peer_allreduce_finalize)" if model._peer is not None
-                  else "NCCL all-reduce of the packed (P, D+1) buffer (peer memory unavailable: %s)" % getattr(model, "_peer_error", None))
+                  "cross-rank sum fused into the finalize kernel over NVLink peer memory (pacoh_peer_allreduce_finalize)" if peer is not None
+                  else "NCCL all-reduce of the packed gradient buffer")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        fn()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -194,141 +285,161 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    # ---- device-resident timing (value)
-    step_dev = lambda: model.svgd_step(model._sample_task_indices())   # noqa: E731
-    for _ in range(args.warmup):
-        step_dev()
+    # ---- device-resident timing (value): K steps of the meta_fit loop body (CUDA-graph replayed where the learner supports it)
+    model.run_steps(args.warmup)
+    K_graph = getattr(model, "GRAPH_STEPS", 0)
+    if K_graph:                                   # capture (if any) happens outside the timed region
+        model.run_steps(2 * K_graph)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    with eng.StageTiming() as stg:
-        ms_total = timed(step_dev, args.steps)
-        stage_ms, stage_calls = stg.read()
+    ms_total = timed(lambda: model.run_steps(args.steps))
     clock_info = clocks.stop() if rank == 0 else None
-    eng.check_info(model._last_info)
+    model._failures.check()
     ms_per_step = ms_total / args.steps
     value = P * T / (ms_per_step * 1e-3)
+    graphed = getattr(model, "_graph", None) is not None
 
-    # ---- end-to-end through the public API with host buffers (e2e)
-    Xh = model.engine.x.cpu().pin_memory()
-    Yh = model.engine.y.cpu().pin_memory()
-    # pipelined like a real input pipeline: two pinned staging sets; while step k runs on the device the host samples and
-    # gathers batch k+1, then reads step k's logp (device->host copy issued every step, waited for one step later)
+    # ---- per-kernel stage times (roofline): a short EAGER region with CUDA events recorded inside the C-ABI call
+    os.environ["PACOH_GRAPH"] = "0"
+    n_stage = max(2, min(args.steps, 10))
+    with eng.StageTiming() as stg:
+        ms_eager = timed(lambda: model.run_steps(n_stage)) / n_stage
+        stage_ms, stage_calls = stg.read()
+    n_kern, n_own, own_names = count_kernels(lambda: model.run_steps(1))
+
+    # ---- end-to-end through the public API with HOST buffers: every step copies its sampled batch H2D from pinned memory
+    #      and reads its result (logp / loss) back D2H
+    Xh, Yh = model.engine.x.cpu().pin_memory(), model.engine.y.cpu().pin_memory()
     lo_e, hi_e = eng.shard_bounds(T, rank, world)
-    xb = [torch.empty((hi_e - lo_e,) + tuple(Xh.shape[1:]), dtype=Xh.dtype).pin_memory() for _ in range(2)]
-    yb = [torch.empty((hi_e - lo_e,) + tuple(Yh.shape[1:]), dtype=Yh.dtype).pin_memory() for _ in range(2)]
-    pending = [None, None]
-    e2e_count = [0]
-    logp_sink = [0.0]
+    e2e_steps = args.steps
+    sink = [0.0]
+    if cfg["kind"] == "svgd":
+        xb = [torch.empty((hi_e - lo_e,) + tuple(Xh.shape[1:]), dtype=Xh.dtype).pin_memory() for _ in range(2)]
+        yb = [torch.empty((hi_e - lo_e,) + tuple(Yh.shape[1:]), dtype=Yh.dtype).pin_memory() for _ in range(2)]
+        pending, cnt = [None, None], [0]
 
-    def step_e2e():
-        k = e2e_count[0] & 1
-        if pending[k] is not None:                      # staging set k was last used two steps ago: its step must be done
-            out, ev = pending[k]
-            ev.synchronize()
-            logp_sink[0] += float(out[0])               # the host really reads the result
-        idx = torch.from_numpy(model._sample_task_indices()[lo_e:hi_e])
-        torch.index_select(Xh, 0, idx, out=xb[k])       # host-side gather of this rank's shard of the sampled batch (the
-        torch.index_select(Yh, 0, idx, out=yb[k])       # reference passes the sampled task tensors themselves, GPR_meta_svgd.py:102-103)
-        pending[k] = model.svgd_step_host(xb[k], yb[k], global_tasks=T, wait=False)   # H2D, full step, D2H of logp
-        e2e_count[0] += 1
-
-    def drain_e2e():
-        for k in range(2):
+        def step_e2e():          # 2-deep pipelined: batch k+1 is gathered on the host while step k runs
+            k = cnt[0] & 1
             if pending[k] is not None:
                 out, ev = pending[k]
                 ev.synchronize()
-                logp_sink[0] += float(out[0])
-                pending[k] = None
+                sink[0] += float(out[0])
+            idx = torch.from_numpy(model._sample_task_indices()[lo_e:hi_e])
+            torch.index_select(Xh, 0, idx, out=xb[k])
+            torch.index_select(Yh, 0, idx, out=yb[k])
+            pending[k] = model.svgd_step_host(xb[k], yb[k], global_tasks=T, wait=False)
+            cnt[0] += 1
 
-    for _ in range(max(3, args.warmup // 2)):
+        def drain():
+            for k in range(2):
+                if pending[k] is not None:
+                    out, ev = pending[k]
+                    ev.synchronize()
+                    sink[0] += float(out[0])
+                    pending[k] = None
+    else:
+        xb = torch.empty((hi_e - lo_e,) + tuple(Xh.shape[1:]), dtype=Xh.dtype).pin_memory()
+        yb = torch.empty((hi_e - lo_e,) + tuple(Yh.shape[1:]), dtype=Yh.dtype).pin_memory()
+        ident = np.arange(T, dtype=np.int32)
+
+        def step_e2e():          # gather on the host, H2D into the engine's task arrays, one step on them, loss back to the host
+            idx_all = model.rds_numpy.choice(cfg["T_total"], size=T)
+            idx = torch.from_numpy(idx_all[lo_e:hi_e])
+            torch.index_select(Xh, 0, idx, out=xb)
+            torch.index_select(Yh, 0, idx, out=yb)
+            model.engine.x[lo_e:hi_e].copy_(xb, non_blocking=True)
+            model.engine.y[lo_e:hi_e].copy_(yb, non_blocking=True)
+            loss = model.map_step(ident) if cfg["kind"] == "map" else model.vi_step(ident)
+            sink[0] += float(loss.item())
+
+        def drain():
+            pass
+
+    for _ in range(3):
         step_e2e()
-    drain_e2e()
-    e2e_steps = args.steps
+    drain()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
-    drain_e2e()
+    drain()
     barrier()
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = P * T / (e2e_ms.item() / e2e_steps * 1e-3)
-    h2d = (T // world) * N_PTS * (D_IN + 1) * 4
-    d2h = P * 4
+    h2d = (hi_e - lo_e) * n * (D_IN + 1) * 4
+    d2h = P * 4 if cfg["kind"] == "svgd" else 4
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (live CUDA-event stage timing inside the timed region)
+    # ---- roofline of the dominant kernel
     ffma_peak = eng.ffma_peak_tflops()
     nominal = 148 * 128 * 2 * 1.965e9 / 1e12
-    evals_rank = P * (T // world)
+    evals_rank = P * (hi_e - lo_e)
+    kf = kernel_flops(n)
     kernels = {}
-    for name, fl in KERNEL_FLOPS.items():
+    for name, fl in kf.items():
         ms = stage_ms[name] / max(stage_calls, 1)
-        tf = fl() * evals_rank / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        kernels[name] = {"ms_per_launch": ms, "algorithmic_gflop_per_launch": fl() * evals_rank / 1e9, "tflops": tf,
-                         "frac_of_fp32_peak": tf / ffma_peak, "share_of_step": ms / ms_per_step}
-    kernels["reduce"] = {"ms_per_launch": stage_ms["reduce"] / max(stage_calls, 1), "share_of_step": stage_ms["reduce"] / max(stage_calls, 1) / ms_per_step}
-    dom = max(KERNEL_FLOPS, key=lambda k: kernels[k]["ms_per_launch"])
+        tf = fl * evals_rank / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        kernels[name] = {"ms_per_launch": ms, "algorithmic_gflop_per_launch": fl * evals_rank / 1e9, "tflops": tf,
+                         "frac_of_fp32_peak": tf / ffma_peak, "share_of_step": ms / ms_eager}
+    kernels["reduce"] = {"ms_per_launch": stage_ms["reduce"] / max(stage_calls, 1), "share_of_step": stage_ms["reduce"] / max(stage_calls, 1) / ms_eager}
+    dom = max(kf, key=lambda k: kernels[k]["ms_per_launch"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            traffic = json.load(open(tpath)).get("config%d" % args.config, {}).get(dom)
         except Exception:
             traffic = None
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
     roofline = {"bound": "fp32", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": ffma_peak, "unit": "TFLOP/s",
                 "frac": kernels[dom]["tflops"] / ffma_peak, "traffic": traffic,
-                "peak_source": "FFMA micro-benchmark run in this process (pacoh_ffma_peak_launch); MEASURED_PEAKS.json holds no FP32 "
+                "peak_source": "FP32 FFMA micro-benchmark run in this process (pacoh_ffma_peak_launch); MEASURED_PEAKS.json holds no FP32 "
                                "figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s" % nominal,
-                "bound_note": "FP32-compute bound (arithmetic intensity ~5e4 FLOP/B, DRAM ~1% busy). All three kernels run their "
-                              "matrix work on tcgen05 in 3xTF32 (fp32-accurate): the MLP hidden-layer and weight-gradient "
-                              "contractions and the rank-4 Gauss-Jordan updates of the GP kernel; tanh / exp2 / the 4x4 pivot-block "
-                              "inverses / row sums run on the CUDA cores. Fractions are ALGORITHMIC fp32 FLOPs over the measured FP32 "
-                              "FFMA peak (the honest denominator for an fp32-parity path), so a kernel can exceed what FFMA alone "
-                              "could reach",
-                "step_achieved_tflops": value * flops_per_eval() / 1e12, "step_frac_of_fp32_peak": value * flops_per_eval() / 1e12 / ffma_peak,
+                "bound_note": "compute bound. Fractions are ALGORITHMIC fp32 FLOPs (SURVEY 8(d)) over the measured FP32 FFMA peak -- the honest "
+                              "denominator for an fp32-parity path; the matrix work runs on tcgen05 in 3xTF32 (3 tensor passes per fp32 "
+                              "product), so a kernel can exceed what FFMA alone could reach (config 5 does)",
+                "timing": "per-kernel CUDA events recorded inside the C-ABI call on the launching stream over a %d-step EAGER region right after "
+                          "the timed region (events cannot be read back from a replayed CUDA graph); eager step %.4f ms vs timed step %.4f ms"
+                          % (n_stage, ms_eager, ms_per_step),
+                "step_achieved_tflops": value * flops_per_eval(n) / 1e12, "step_frac_of_fp32_peak": value * flops_per_eval(n) / 1e12 / ffma_peak,
                 "kernels": kernels}
-    # the driver-measured peaks (HBM copy bandwidth, dense bf16 tensor throughput) for the same kernel, for the record:
-    # neither bounds this path (see bound_note), which is why the FP32 FFMA peak is the denominator above
-    mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(mp_path):
-        try:
-            mp = json.load(open(mp_path))
-            dom_ms = kernels[dom]["ms_per_launch"]
-            vs = {"source": "MEASURED_PEAKS.json"}
-            if traffic and mp.get("hbm_gbs"):
-                gbs = traffic / (dom_ms * 1e-3) / 1e9
-                vs["hbm"] = {"achieved_gbs": gbs, "peak_gbs": mp["hbm_gbs"], "frac": gbs / mp["hbm_gbs"]}
-            tpk = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
-            if tpk:
-                vs["tensor_bf16"] = {"achieved_algorithmic_tflops": kernels[dom]["tflops"], "peak_tflops": tpk,
-                                     "frac": kernels[dom]["tflops"] / tpk,
-                                     "note": "fp32 parity needs 3xTF32: 3 passes at half the bf16 rate, i.e. 6 bf16-equivalent "
-                                             "tensor FLOPs per algorithmic FLOP of the GEMM part"}
-            roofline["vs_measured_peaks"] = vs
-        except Exception:
-            pass
+    tpk = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
+    if tpk:
+        # tensor-pipe view of the same kernel: 3xTF32 = 3 tf32 passes at half the bf16 rate = 6 bf16-equivalent FLOPs per algorithmic FLOP
+        roofline["vs_measured_peaks"] = {"source": "MEASURED_PEAKS.json", "tensor_bf16_peak_tflops": tpk,
+                                         "tensor_equiv_tflops": 6 * kernels[dom]["tflops"], "tensor_frac": 6 * kernels[dom]["tflops"] / tpk,
+                                         "note": "upper bound on the tensor-pipe share: counts every algorithmic FLOP of the kernel as 3xTF32 work"}
+        if traffic and mp.get("hbm_gbs"):
+            gbs = traffic / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
+            roofline["vs_measured_peaks"]["hbm"] = {"achieved_gbs": gbs, "peak_gbs": mp["hbm_gbs"], "frac": gbs / mp["hbm_gbs"]}
 
-    # ---- CPU baseline (oracle port) on the host cores, bounded sample, N = 1 only
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference_steps(steps=8, warmup=1, data=data[:CPU_SLICE_T])
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d-task slice of the 4096-task batch per step (64 particles x 50 points), 8 steps, %.2f s/step" % (CPU_SLICE_T, sec)}
+        cpu = cpu_baseline_dict(cfg, data[:max(cfg["cpu_T"], 2)], quick=args.config == 5)
 
-    launches_per_step = 3 + 3 + 1 + 3 + 1      # mlp_fwd, gp_mll, mlp_bwd | 2 partial reductions + hyp reduction | finalize | svgd x3 | adam
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config_dict(world), collective=collective),
+            "data": "synthetic", "config": config_dict(cfg, world, {"collective": collective, "cuda_graph": "%d steps per replayed graph" % K_graph if graphed else "eager launches"}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms.item() / e2e_steps, "timing": "host wall clock around K steps (2-deep pipelined: batch k+1 is gathered on the host while step k runs; every step copies its batch H2D from pinned memory and its logp D2H), barrier + synchronize on both sides"},
-            "gpu_launches": launches_per_step * args.steps, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}
+                    "ms_per_step": e2e_ms.item() / e2e_steps,
+                    "timing": "host wall clock around K steps through the learner's public step call with HOST batches: every step gathers "
+                              "its sampled batch on the host into pinned memory, copies it H2D and reads its logp / loss D2H; barrier + "
+                              "synchronize on both sides" + ("; 2-deep pipelined (batch k+1 is gathered while step k runs)" if cfg["kind"] == "svgd" else "")},
+            "gpu_launches": n_kern * args.steps,
+            "gpu_launches_note": "%d kernels per step counted with the torch profiler (CUPTI) on one eager step, %d of them from libpacoh_b200 "
+                                 "(%s); a replayed graph launches the same kernels" % (n_kern, n_own, ", ".join(own_names)[:600]),
+            "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -339,6 +450,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
+    ap.add_argument("--points", type=int, default=2048, help="points per task of config 5 (512 / 1024 / 2048)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -144,6 +144,15 @@ int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const void* const
                                   const float* prior_sigma, float prior_factor, float pre_factor, float* logp,
                                   float* dtheta, void* stream);
 
+/* The same with the token taken from the device: token_dev (int32, device, may be NULL) is the step counter of a
+ * CUDA-graph-captured training loop (pacoh_step_prepare) and the token of this call is *token_dev + token.  err_flag
+ * (int32, device, may be NULL) is set non-zero if a peer never announced within the bounded wait (a dead rank): the
+ * kernel then returns garbage sums instead of hanging the node. */
+int pacoh_peer_allreduce_finalize_dev(int32_t world, int32_t rank, const void* const* peer_bufs, void* const* peer_flags,
+                                      uint32_t token, const void* token_dev, int32_t* err_flag, int32_t P, int64_t D,
+                                      const float* theta, const float* prior_mu, const float* prior_sigma, float prior_factor,
+                                      float pre_factor, float* logp, float* dtheta, void* stream);
+
 /*
  * SVGD direction (SVGD.phi tail + RBF_Kernel, svgd.py:18-21,32-59,103-107):
  *   d2_ij = |theta_i|^2 + |theta_j|^2 - 2 theta_i.theta_j ;  gamma = 1/(1e-8 + 2 h^2)
@@ -190,6 +199,22 @@ int pacoh_vi_grad(int32_t S, int64_t D, const float* scale, const float* eps, co
  */
 int pacoh_adam_step(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg, float* exp_avg_sq,
                     float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/*
+ * Device-side step state for training loops captured in a CUDA graph (the meta_fit loops GPR_meta_svgd.py:100-104,
+ * GPR_meta_vi.py:103-110, GPR_meta_mll.py:104-117: sample a batch, step, optimizer.step(), lr_scheduler.step()).
+ * `state` = 8 x 4 bytes on the device, zero-initialised: [0] int32 number of completed steps, [2] float learning rate,
+ * [3] float lr / (1 - beta1^step), [4] float 1 / sqrt(1 - beta2^step).
+ * pacoh_step_prepare: step += 1; lr = lr0 * gamma^((step - 1) / decay_every) (torch StepLR; decay_every <= 0: constant);
+ * copies slot (old step mod K) of idx_stream (K, T) int32 to idx_out (T) and of fstream (K, F) to fout (F) (either may be
+ * NULL): the host uploads K steps' worth of sampled task indices (numpy RandomState.choice stream) / normal draws at once.
+ * pacoh_adam_step_dev: pacoh_adam_step with lr and bias corrections read from `state`.
+ */
+int pacoh_step_prepare(void* state, int32_t K, int32_t T, const int32_t* idx_stream, int32_t* idx_out, int64_t F,
+                       const float* fstream, float* fout, float lr0, float gamma, int32_t decay_every, float beta1, float beta2,
+                       void* stream);
+int pacoh_adam_step_dev(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg, float* exp_avg_sq,
+                        float beta1, float beta2, float eps, const void* state, void* stream);
 
 /*
  * Host-only helper: the persistent schedule of the tensor-core MLP backward kernel (one CTA per SM per wave, the

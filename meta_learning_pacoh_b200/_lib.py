@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_meta_mll_fwd_bwd_ragged", "pacoh_mlp_bwd_schedule", "pacoh_logprob_finalize", "pacoh_peer_allreduce_finalize", "pacoh_svgd_workspace_bytes",
     "pacoh_svgd_phi", "pacoh_svgd_kernel_matrix", "pacoh_svgd_phi_apply", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
     "pacoh_stage_timing_enable", "pacoh_stage_timing_read", "pacoh_gp_forward", "pacoh_gp_forward_workspace_bytes",
-    "pacoh_debug_big_layout",
+    "pacoh_debug_big_layout", "pacoh_peer_allreduce_finalize_dev", "pacoh_step_prepare", "pacoh_adam_step_dev",
 ]
 
 
@@ -73,6 +73,12 @@ def _load():
     lib.pacoh_logprob_finalize.argtypes = [i32, i64, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp]
     lib.pacoh_peer_allreduce_finalize.restype = ctypes.c_int
     lib.pacoh_peer_allreduce_finalize.argtypes = [i32, i32, vp, vp, ctypes.c_uint32, i32, i64, vp, vp, vp, f32, f32, vp, vp, vp]
+    lib.pacoh_peer_allreduce_finalize_dev.restype = ctypes.c_int
+    lib.pacoh_peer_allreduce_finalize_dev.argtypes = [i32, i32, vp, vp, ctypes.c_uint32, vp, vp, i32, i64, vp, vp, vp, f32, f32, vp, vp, vp]
+    lib.pacoh_step_prepare.restype = ctypes.c_int
+    lib.pacoh_step_prepare.argtypes = [vp, i32, i32, vp, vp, i64, vp, vp, f32, f32, i32, f32, f32, vp]
+    lib.pacoh_adam_step_dev.restype = ctypes.c_int
+    lib.pacoh_adam_step_dev.argtypes = [i64, vp, vp, f32, vp, vp, f32, f32, f32, vp, vp]
     lib.pacoh_svgd_workspace_bytes.restype = i64
     lib.pacoh_svgd_workspace_bytes.argtypes = [i32, i64]
     lib.pacoh_svgd_phi.restype = ctypes.c_int

@@ -101,17 +101,28 @@ __device__ __forceinline__ float ld_peer(const float* p) {      // peer data: ne
   return v;
 }
 
-__global__ void peer_sum_finalize_kernel(PeerPtrs pp, int world, int rank, unsigned int token, int P, int64_t D,
+// `token_dev` (optional): the step counter of a CUDA-graph-captured training loop (pacoh_step_prepare); the token of this
+// call is then *token_dev + token (token = offset).  The wait is bounded: a peer that never announces (a rank that died or
+// raised) trips `*err_flag` after 30 s instead of hanging the node; the sums are then garbage and the
+// host raises on its next check.
+__global__ void peer_sum_finalize_kernel(PeerPtrs pp, int world, int rank, unsigned int token, const int* __restrict__ token_dev,
+                                         int* __restrict__ err_flag, int P, int64_t D,
                                          const float* __restrict__ theta, const float* __restrict__ mu,
                                          const float* __restrict__ sigma, float prior_factor, float pre_factor,
                                          float* __restrict__ logp, float* __restrict__ dtheta) {
   __shared__ float red[32];
+  if (token_dev != nullptr) token += (unsigned int)*token_dev;
   if (threadIdx.x < world) {
     if (blockIdx.x == 0) {
       __threadfence_system();                                     // the kernels before us on this stream wrote the buffer
       st_release_sys(pp.flag[threadIdx.x] + rank, token);
     }
-    while ((int)(ld_acquire_sys(pp.flag[rank] + threadIdx.x) - token) < 0) { }
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(ld_acquire_sys(pp.flag[rank] + threadIdx.x) - token) < 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 30000000000ull) { if (err_flag != nullptr) atomicExch(err_flag, 1 + (int)threadIdx.x); break; }   // 30 s
+    }
   }
   __syncthreads();
   const int p = blockIdx.x;
@@ -192,6 +203,46 @@ __global__ void adam_kernel(int64_t count, float* __restrict__ p, const float* _
   p[i] -= step_size * (mi / denom);
 }
 
+// Same update with the step-dependent scalars read from the device-side step state (CUDA-graph-captured loops).
+__global__ void adam_dev_kernel(int64_t count, float* __restrict__ p, const float* __restrict__ g, float gsign,
+                                float* __restrict__ m, float* __restrict__ v, float beta1, float beta2, float eps,
+                                const float* __restrict__ state) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float step_size = state[3], inv_sqrt_bc2 = state[4];
+  const float gr = gsign * g[i];
+  const float mi = m[i] + (gr - m[i]) * (1.0f - beta1);
+  const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gr * gr);
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  p[i] -= step_size * (mi / denom);
+}
+
+// One block: advances the step counter, derives the learning rate (StepLR) and Adam's bias corrections for the new step,
+// and copies slot (old step mod K) of the pre-uploaded index / float streams into the fixed buffers the step's kernels read.
+__global__ void step_prepare_kernel(int* __restrict__ state, int K, int T, const int* __restrict__ idx_stream, int* __restrict__ idx_out,
+                                    int64_t F, const float* __restrict__ fstream, float* __restrict__ fout,
+                                    float lr0, float gamma, int decay_every, float beta1, float beta2) {
+  const int s = state[0];
+  __syncthreads();
+  const int slot = K > 0 ? s % K : 0;
+  if (threadIdx.x == 0) {
+    const int step = s + 1;
+    state[0] = step;
+    double lr = (double)lr0;
+    if (decay_every > 0 && gamma != 1.0f) lr *= pow((double)gamma, (double)((step - 1) / decay_every));
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    float* fs = reinterpret_cast<float*>(state);
+    fs[2] = (float)lr;
+    fs[3] = (float)(lr / bc1);
+    fs[4] = (float)(1.0 / sqrt(bc2));
+  }
+  if (idx_stream != nullptr)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) idx_out[t] = idx_stream[(size_t)slot * T + t];
+  if (fstream != nullptr)
+    for (int64_t i = threadIdx.x; i < F; i += blockDim.x) fout[i] = fstream[(size_t)slot * F + i];
+}
+
 }  // namespace
 
 int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,
@@ -226,10 +277,10 @@ extern "C" int pacoh_logprob_finalize(int32_t P, int64_t D, const float* theta, 
   return PACOH_OK;
 }
 
-extern "C" int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const void* const* peer_bufs, void* const* peer_flags,
-                                             uint32_t token, int32_t P, int64_t D, const float* theta, const float* prior_mu,
-                                             const float* prior_sigma, float prior_factor, float pre_factor, float* logp,
-                                             float* dtheta, void* stream) {
+extern "C" int pacoh_peer_allreduce_finalize_dev(int32_t world, int32_t rank, const void* const* peer_bufs, void* const* peer_flags,
+                                                 uint32_t token, const void* token_dev, int32_t* err_flag, int32_t P, int64_t D,
+                                                 const float* theta, const float* prior_mu, const float* prior_sigma,
+                                                 float prior_factor, float pre_factor, float* logp, float* dtheta, void* stream) {
   if (world < 1 || world > PACOH_MAX_PEERS || rank < 0 || rank >= world || !peer_bufs || !peer_flags || P < 1 || D < 1 ||
       !theta || !prior_mu || !prior_sigma || !logp || !dtheta) {
     set_error("pacoh_peer_allreduce_finalize: invalid argument");
@@ -241,10 +292,18 @@ extern "C" int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const 
     pp.flag[r] = r < world ? (unsigned int*)peer_flags[r] : nullptr;
     if (r < world && (!pp.buf[r] || !pp.flag[r])) { set_error("pacoh_peer_allreduce_finalize: null peer pointer"); return PACOH_ERR_INVALID; }
   }
-  peer_sum_finalize_kernel<<<P, 1024, 0, (cudaStream_t)stream>>>(pp, world, rank, token, P, D, theta, prior_mu, prior_sigma,
-                                                                prior_factor, pre_factor, logp, dtheta);
+  peer_sum_finalize_kernel<<<P, 1024, 0, (cudaStream_t)stream>>>(pp, world, rank, token, (const int*)token_dev, err_flag, P, D, theta,
+                                                                prior_mu, prior_sigma, prior_factor, pre_factor, logp, dtheta);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
+}
+
+extern "C" int pacoh_peer_allreduce_finalize(int32_t world, int32_t rank, const void* const* peer_bufs, void* const* peer_flags,
+                                             uint32_t token, int32_t P, int64_t D, const float* theta, const float* prior_mu,
+                                             const float* prior_sigma, float prior_factor, float pre_factor, float* logp,
+                                             float* dtheta, void* stream) {
+  return pacoh_peer_allreduce_finalize_dev(world, rank, peer_bufs, peer_flags, token, nullptr, nullptr, P, D, theta, prior_mu,
+                                           prior_sigma, prior_factor, pre_factor, logp, dtheta, stream);
 }
 
 extern "C" int pacoh_vi_sample(int32_t S, int64_t D, const float* loc, const float* scale, const float* eps, float* theta,
@@ -278,6 +337,31 @@ extern "C" int pacoh_adam_step(int64_t count, float* param, const float* grad, f
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       count, param, grad, grad_sign, exp_avg, exp_avg_sq, beta1, beta2, eps, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)));
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_step_prepare(void* state, int32_t K, int32_t T, const int32_t* idx_stream, int32_t* idx_out, int64_t F,
+                                  const float* fstream, float* fout, float lr0, float gamma, int32_t decay_every, float beta1,
+                                  float beta2, void* stream) {
+  if (!state || K < 0 || T < 0 || F < 0 || (idx_stream && (!idx_out || K < 1)) || (fstream && (!fout || K < 1))) {
+    set_error("pacoh_step_prepare: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  step_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((int*)state, K, T, idx_stream, idx_out, F, fstream, fout, lr0, gamma,
+                                                           decay_every, beta1, beta2);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_adam_step_dev(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg,
+                                   float* exp_avg_sq, float beta1, float beta2, float eps, const void* state, void* stream) {
+  if (count < 1 || !param || !grad || !exp_avg || !exp_avg_sq || !state) {
+    set_error("pacoh_adam_step_dev: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  adam_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(count, param, grad, grad_sign, exp_avg, exp_avg_sq,
+                                                                                    beta1, beta2, eps, (const float*)state);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

@@ -214,8 +214,10 @@ class PinnedRing:
         self._ev = [None] * slots
         self._next = 0
 
-    def upload(self, array):
-        src = torch.from_numpy(np.ascontiguousarray(array))
+    def upload(self, array, out=None):
+        """Returns a device tensor holding `array` (or fills the given device tensor `out`, e.g. the fixed buffer a
+        captured CUDA graph reads); the copy is asynchronous on the current stream."""
+        src = torch.from_numpy(np.ascontiguousarray(array)).reshape(-1)
         assert src.dtype == self.dtype
         k = self._next
         self._next = (k + 1) % self.slots
@@ -225,9 +227,53 @@ class PinnedRing:
             self._buf[k] = torch.empty(max(src.numel(), 16), dtype=self.dtype).pin_memory()
             self._ev[k] = torch.cuda.Event()
         self._buf[k][:src.numel()].copy_(src)
-        out = self._buf[k][:src.numel()].to(self.device, non_blocking=True)
+        if out is None:
+            out = self._buf[k][:src.numel()].to(self.device, non_blocking=True)
+        else:
+            out.view(-1)[:src.numel()].copy_(self._buf[k][:src.numel()], non_blocking=True)
         self._ev[k].record(torch.cuda.current_stream(self.device))
         return out
+
+
+class StepState:
+    """Device-side state of a training loop (pacoh_step_prepare): number of completed steps, current learning rate
+    (StepLR) and Adam's bias corrections.  Every kernel of a step reads these from the device, so the step sequence can
+    be captured in a CUDA graph and replayed without the host touching it; `steps` mirrors the counter on the host."""
+
+    def __init__(self, device, lr, lr_decay=1.0, decay_every=1000, betas=(0.9, 0.999)):
+        self.device = torch.device(device)
+        self.buf = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self.lr, self.gamma, self.decay_every, self.betas = float(lr), float(lr_decay), int(decay_every), betas
+        self.steps = 0                                   # host mirror of buf[0]
+
+    def prepare(self, K=0, T=0, idx_stream=None, idx_out=None, fstream=None, fout=None):
+        F = fout.numel() if fout is not None else 0
+        check(lib.pacoh_step_prepare(_ptr(self.buf), int(K), int(T), _ptr(idx_stream), _ptr(idx_out), int(F), _ptr(fstream), _ptr(fout),
+                                     self.lr, self.gamma, self.decay_every if self.gamma < 1.0 else 0, float(self.betas[0]),
+                                     float(self.betas[1]), _stream()))
+        self.steps += 1
+
+
+class StepGraph:
+    """`k` consecutive training steps captured in one CUDA graph ("CUDA-graph capture of the whole step").
+    `step_fn` must be capture-safe: no host synchronisation, everything step-dependent read from device memory
+    (StepState, pre-uploaded index streams).  It is run eagerly once on a side stream before the capture (lazy
+    initialisations, workspace allocations), which COUNTS as real steps -- callers account for `warm_steps`."""
+
+    def __init__(self, step_fn, k, device, warm=True):
+        self.k, self.device = int(k), torch.device(device)
+        self.graph = torch.cuda.CUDAGraph()
+        self.warm_steps = 0
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+                self.out = [step_fn() for _ in range(self.k)]
+        torch.cuda.current_stream(self.device).wait_stream(side)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out[-1]
 
 
 class FailureFlag:
@@ -293,6 +339,7 @@ class PeerAllReduce:
         self._bufs = [(ctypes.c_void_p * self.world)(*[b + 4 * h * self.n_pad for b in bases]) for h in range(2)]
         self._flags = (ctypes.c_void_p * self.world)(*[b + 4 * 2 * self.n_pad for b in bases])
         self.token = 0
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)   # set by the kernel if a peer never announced (30 s)
         torch.cuda.synchronize(self.device)
         dist.barrier(group)                              # every rank's flags are zero before anyone announces
 
@@ -301,27 +348,35 @@ class PeerAllReduce:
         h = (self.token + 1) & 1
         return self.local[h * self.n_pad:h * self.n_pad + self.n]
 
-    def finalize(self, theta, prior_mu, prior_sigma, prior_factor, pre):
+    def finalize(self, theta, prior_mu, prior_sigma, prior_factor, pre, token_dev=None):
+        """``token_dev``: int32 device tensor whose element 0 holds this call's token (the step counter of a StepState
+        that the caller keeps in lock-step with ``self.token``): lets the call sit inside a captured CUDA graph.  The
+        buffer parity is still chosen on the host, so a graph must hold an EVEN number of steps."""
         self.token += 1
         h = self.token & 1
         P, D = theta.shape
         assert (P, D) == (self.P, self.D)
         logp = torch.empty(P, dtype=torch.float32, device=self.device)
         dtheta = torch.empty(P, D, dtype=torch.float32, device=self.device)
-        check(lib.pacoh_peer_allreduce_finalize(self.world, self.rank, self._bufs[h], self._flags, self.token & 0xFFFFFFFF, P, D,
-                                                _ptr(theta), _ptr(prior_mu), _ptr(prior_sigma), float(prior_factor), float(pre),
-                                                _ptr(logp), _ptr(dtheta), _stream()))
+        tok = 0 if token_dev is not None else self.token & 0xFFFFFFFF
+        check(lib.pacoh_peer_allreduce_finalize_dev(self.world, self.rank, self._bufs[h], self._flags, tok, _ptr(token_dev),
+                                                    _ptr(self.err), P, D, _ptr(theta), _ptr(prior_mu), _ptr(prior_sigma),
+                                                    float(prior_factor), float(pre), _ptr(logp), _ptr(dtheta), _stream()))
         return logp, dtheta
 
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("peer all-reduce: rank %d never announced its buffer within 30 s (dead or failed rank)" % (int(self.err.item()) - 1))
 
-def meta_log_prob_and_score(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None, peer=None):
+
+def meta_log_prob_and_score(theta, engine, task_idx, prior_mu, prior_sigma, prior_factor, pre, group=None, peer=None, token_dev=None):
     """(logp (P,), score = d logp / d theta (P, D), info) without autograd: what SVGD.phi needs (svgd.py:13-16).
     ``task_idx`` is this rank's shard when ``group`` is given; ``pre`` is computed from the GLOBAL batch.  With a
     ``PeerAllReduce`` the cross-rank sum runs over NVLink peer memory inside the finalize kernel, else as one NCCL
     all-reduce of the packed buffer."""
     if peer is not None:
         _, _, info = engine.mll_fwd_bwd(theta, task_idx, want_mll=False, want_info=True, out=peer.out_buffer())
-        logp, dtheta = peer.finalize(theta, prior_mu, prior_sigma, prior_factor, pre)
+        logp, dtheta = peer.finalize(theta, prior_mu, prior_sigma, prior_factor, pre, token_dev=token_dev)
         return logp, dtheta, info
     _, packed, info = engine.mll_fwd_bwd(theta, task_idx, want_mll=False, want_info=True)
     if group is not None:
@@ -520,7 +575,10 @@ class PacohAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
 
     @torch.no_grad()
-    def step(self, direction=None):
+    def step(self, direction=None, state=None):
+        """``state``: a StepState already advanced for this step (pacoh_step_prepare): the learning rate and the bias
+        corrections are then read on the device (pacoh_adam_step_dev) -- the form a captured CUDA graph needs.  The host
+        copies of ``step`` / ``lr`` are kept in sync by the caller (sync_from)."""
         for group in self.param_groups:
             for p in group["params"]:
                 g, sign = (direction, -1.0) if direction is not None else (p.grad, 1.0)
@@ -531,11 +589,22 @@ class PacohAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
                 b1, b2 = group["betas"]
                 assert p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32
+                if state is not None:
+                    check(lib.pacoh_adam_step_dev(p.numel(), _ptr(p), _ptr(g), sign, _ptr(st["exp_avg"]), _ptr(st["exp_avg_sq"]),
+                                                  float(b1), float(b2), float(group["eps"]), _ptr(state.buf), _stream()))
+                    continue
+                st["step"] += 1
                 check(lib.pacoh_adam_step(p.numel(), _ptr(p), _ptr(g), sign, _ptr(st["exp_avg"]), _ptr(st["exp_avg_sq"]),
                                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), int(st["step"]), _stream()))
+
+    def sync_from(self, state):
+        """Host bookkeeping after device-state steps: torch-compatible ``step`` counts (state_dict round trips)."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p in self.state and len(self.state[p]):
+                    self.state[p]["step"] = state.steps
 
 
 class StageTiming:

@@ -115,11 +115,7 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
             if n_iter is None:
                 n_iter = self.num_iter_fit
             for itr in range(1, n_iter + 1):
-                self.optimizer.zero_grad()
-                task_idx = self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size)
-                loss = self._loss_and_grad(task_idx)
-                self.optimizer.step()
-                self.lr_scheduler.step()
+                loss = self.map_step(self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size))
                 cum_loss = cum_loss + loss
                 if itr == 1 or itr % log_period == 0:
                     self._failures.check()
@@ -139,10 +135,43 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         self.fitted = True
         return loss.item()
 
+    def map_step(self, task_idx):
+        """One iteration of the meta_fit loop body on the given batch (GPR_meta_mll.py:107-117): zero_grad, loss = - sum of the
+        batch's MLLs, backward, optimizer step, lr schedule.  Returns the loss (device scalar)."""
+        self.optimizer.zero_grad()
+        loss = self._loss_and_grad(task_idx)
+        self.optimizer.step()
+        self.lr_scheduler.step()
+        return loss
+
+    def run_steps(self, n):
+        loss = None
+        for _ in range(n):
+            loss = self.map_step(self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size))
+        return loss
+
+    def shard_tasks(self, group=None):
+        """Task-shard every sampled batch over the ranks of ``group``: all ranks hold the same model and draw
+        the same batch; each evaluates a contiguous slice and the packed (D + 1) buffer (gradient | sum of MLLs) is summed
+        with one NCCL all-reduce."""
+        import torch.distributed as dist
+        assert dist.is_initialized()
+        self._group = group if group is not None else dist.group.WORLD
+        self._rank, self._world = dist.get_rank(self._group), dist.get_world_size(self._group)
+        return self
+
     def _loss_and_grad(self, task_idx):
-        idx = self._idx_ring.upload(np.asarray(task_idx, dtype=np.int32))
+        task_idx = np.asarray(task_idx, dtype=np.int32)
+        world, rank = getattr(self, "_world", 1), getattr(self, "_rank", 0)
+        if world > 1:
+            assert len(task_idx) >= world, "task batch smaller than the number of ranks"
+            lo, hi = eng.shard_bounds(len(task_idx), rank, world)
+            task_idx = task_idx[lo:hi]
+        idx = self._idx_ring.upload(task_idx)
         theta = self._pack()
         _, packed, info = self.engine.mll_fwd_bwd(theta, idx, want_mll=False, want_info=True)
+        if world > 1:
+            torch.distributed.all_reduce(packed, group=self._group)
         D = self.arch.D
         self._scatter_grad(-packed[:D])                 # loss = - sum_t mll_t
         self._last_info = info

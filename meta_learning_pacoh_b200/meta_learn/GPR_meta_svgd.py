@@ -79,6 +79,9 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
             if ok.item() < 1:
                 self._peer = None
+        self._graph = None
+        if self._peer is not None and self._state is not None:
+            self._peer.token = self._state.steps       # the kernel's token is the device step count; the host copy picks the buffer parity
         return self
 
     # ------------------------------------------------------------------ training
@@ -88,10 +91,12 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         t = time.time()
         if n_iter is None:
             n_iter = self.num_iter_fit
-        for itr in range(1, n_iter + 1):
-            task_idx = self._sample_task_indices()
-            self.svgd_step(task_idx)
-            self.lr_scheduler.step()
+        itr = 0
+        while itr < n_iter:
+            # run up to the next logging point (iteration 1 and every multiple of log_period, GPR_meta_svgd.py:106)
+            nxt = 1 if itr == 0 else min(n_iter, (itr // log_period + 1) * log_period)
+            self.run_steps(nxt - itr)
+            itr = nxt
             if itr == 1 or itr % log_period == 0:
                 self._failures.check()
                 duration = time.time() - t
@@ -105,28 +110,93 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         self._failures.check()
         self.fitted = True
 
+    # One code path for eager and graph-captured steps: everything step-dependent (Adam's step count and bias
+    # corrections, the StepLR learning rate, the cross-rank token, the sampled task indices) is read from DEVICE memory
+    # (engine.StepState / pacoh_step_prepare), so the same call sequence can be replayed from a CUDA graph.
+    def _device_step(self, engine, idx_cur, K, idx_stream, pre):
+        st = self._state
+        st.prepare(K, idx_cur.numel(), idx_stream, idx_cur)
+        self._phi.prepare(self.particles)                              # K(theta) on a side stream, under the MLL kernels
+        logp, score, info = eng.meta_log_prob_and_score(self.particles, engine, idx_cur, self._prior_mu, self._prior_sigma,
+                                                        self.prior_factor, pre, self._group, self._peer,
+                                                        token_dev=st.buf if self._peer is not None else None)
+        phi = self._phi(self.particles, score)
+        self.optimizer.step(direction=phi, state=st)                   # grad = -phi (svgd.py:27)
+        self._failures.update(info)
+        return logp, info
+
     def svgd_step(self, task_idx):
         """One SVGD update on the sampled batch (closure svgd_step, GPR_meta_svgd.py:190-199 -> svgd.py:25-28).
-        ``task_idx``: numpy / sequence of task indices into the meta-training set (with repetitions)."""
+        ``task_idx``: numpy / sequence of task indices into the meta-training set (with repetitions); the reference's
+        closure receives the sampled task dicts themselves -- ``svgd_step_host`` is the variant fed with the tensors."""
         idx = np.asarray(task_idx, dtype=np.int32)
         T = idx.shape[0]
         assert T >= self._world, "task batch (%d) smaller than the number of ranks (%d): every rank needs a task" % (T, self._world)
         lo, hi = eng.shard_bounds(T, self._rank, self._world)
-        idx_dev = self._idx_ring.upload(idx[lo:hi])
         pre = eng.pre_factor(self.task_sizes[idx])                     # GLOBAL batch, harmonic mean of its n_t (random_gp.py:209-212)
-        self._phi.prepare(self.particles)                              # K(theta) on a side stream, under the MLL kernels
-        logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
-                                                        self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
-        phi = self._phi(self.particles, score)
-        if isinstance(self.optimizer, eng.PacohAdam):
-            self.optimizer.step(direction=phi)                         # grad = -phi (svgd.py:27)
-        else:
+        if self._state is None:                                        # optimizer='SGD': host-side step (no device state)
+            idx_dev = self._idx_ring.upload(idx[lo:hi])
+            self._phi.prepare(self.particles)
+            logp, score, info = eng.meta_log_prob_and_score(self.particles, self.engine, idx_dev, self._prior_mu,
+                                                            self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
+            phi = self._phi(self.particles, score)
             self.optimizer.zero_grad()
             self.particles.grad = -phi
             self.optimizer.step()
+            self._failures.update(info)
+        else:
+            if self._idx_cur is None or self._idx_cur.numel() != hi - lo:
+                self._idx_cur = torch.empty(hi - lo, dtype=torch.int32, device=self.device)
+                self._graph = None
+            stream = self._idx_ring.upload(idx[lo:hi])
+            logp, info = self._device_step(self.engine, self._idx_cur, 1, stream, pre)
+            self.optimizer.sync_from(self._state)
         self._last_info, self._last_logp = info, logp
-        self._failures.update(info)
         return logp
+
+    GRAPH_STEPS = 10     # training steps per captured CUDA graph (even: the peer buffers alternate by step parity)
+
+    def run_steps(self, n):
+        """``n`` meta-training steps (sample a batch with replacement, svgd_step, lr schedule) -- the body of the reference's
+        meta_fit loop (GPR_meta_svgd.py:100-104).  With the Adam optimizer and equally sized tasks, GRAPH_STEPS steps at a
+        time are replayed from one CUDA graph whose kernels read the step state and the pre-uploaded index stream (the same
+        numpy RandomState.choice draws, in the same order) from the device; PACOH_GRAPH=0 keeps every step eager.  Both
+        forms launch the same kernels in the same order."""
+        K = self.GRAPH_STEPS
+        use_graph = (self._state is not None and not self._ragged and os.environ.get("PACOH_GRAPH", "1") != "0")
+        while n > 0:
+            if use_graph and n >= K and self._state.steps % 2 == 0 and self._state.steps > 0 and self._idx_cur is not None \
+                    and self._idx_cur.numel() == self._local_batch():
+                lo, hi = eng.shard_bounds(self.task_batch_size, self._rank, self._world)
+                if self._graph is None:
+                    self._idx_stream = torch.zeros(K, hi - lo, dtype=torch.int32, device=self.device)
+                    pre = eng.pre_factor(self.task_sizes[:1].repeat(self.task_batch_size))
+                    s0, t0 = self._state.steps, (self._peer.token if self._peer is not None else 0)
+                    self._graph = eng.StepGraph(lambda: self._device_step(self.engine, self._idx_cur, K, self._idx_stream, pre), K, self.device)
+                    self._state.steps = s0                          # the capture only recorded: nothing ran
+                    if self._peer is not None:
+                        self._peer.token = t0
+                s0 = self._state.steps
+                rows = np.empty((K, hi - lo), dtype=np.int32)
+                for j in range(K):                                   # row (step mod K) = the batch of that step
+                    rows[(s0 + j) % K] = self._sample_task_indices()[lo:hi]
+                self._idx_ring.upload(rows, out=self._idx_stream)
+                self._last_logp, self._last_info = self._graph.replay()
+                self._state.steps += K
+                if self._peer is not None:
+                    self._peer.token += K
+                self.optimizer.sync_from(self._state)
+                for _ in range(K):
+                    self.lr_scheduler.step()
+                n -= K
+            else:
+                self.svgd_step(self._sample_task_indices())
+                self.lr_scheduler.step()
+                n -= 1
+
+    def _local_batch(self):
+        lo, hi = eng.shard_bounds(self.task_batch_size, self._rank, self._world)
+        return hi - lo
 
     def svgd_step_host(self, x_batch, y_batch, global_tasks=None, wait=True):
         """Same update as svgd_step, fed like the reference's closure is (GPR_meta_svgd.py:190-199 receives the sampled
@@ -174,18 +244,19 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
             self._copy_event[slot].record(self._copy_stream)
         torch.cuda.current_stream(self.device).wait_event(self._copy_event[slot])
         pre = eng.pre_factor([se.n] * T)
-        self._phi.prepare(self.particles)
-        logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx[slot], self._prior_mu,
-                                                        self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
-        phi = self._phi(self.particles, score)
-        if isinstance(self.optimizer, eng.PacohAdam):
-            self.optimizer.step(direction=phi)
+        if self._state is not None:
+            logp, info = self._device_step(se, self._stage_idx[slot], 0, None, pre)
+            self.optimizer.sync_from(self._state)
         else:
+            self._phi.prepare(self.particles)
+            logp, score, info = eng.meta_log_prob_and_score(self.particles, se, self._stage_idx[slot], self._prior_mu,
+                                                            self._prior_sigma, self.prior_factor, pre, self._group, self._peer)
+            phi = self._phi(self.particles, score)
             self.optimizer.zero_grad()
             self.particles.grad = -phi
             self.optimizer.step()
+            self._failures.update(info)
         self._last_info = info
-        self._failures.update(info)
         out, ev = self._logp_host[slot], self._logp_event[slot]
         out.copy_(logp, non_blocking=True)
         ev.record(torch.cuda.current_stream(self.device))
@@ -239,8 +310,10 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
 
     def _setup_optimizer(self, optimizer, lr, lr_decay):
         assert hasattr(self, 'particles'), "SVGD must be initialized before setting up optimizer"
+        self._state, self._graph, self._idx_cur = None, None, None
         if optimizer == 'Adam':
             self.optimizer = eng.PacohAdam([self.particles], lr=lr)
+            self._state = eng.StepState(self.device, lr, lr_decay)     # lr, StepLR(1000, lr_decay) and Adam's step count on the device
         elif optimizer == 'SGD':
             self.optimizer = torch.optim.SGD([self.particles], lr=lr)
         else:

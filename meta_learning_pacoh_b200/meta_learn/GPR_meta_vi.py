@@ -8,6 +8,7 @@
 boundary table in SURVEY 8(b) specifies.
 """
 import math
+import os
 import time
 
 import numpy as np
@@ -115,12 +116,11 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
         if n_iter is None:
             n_iter = self.num_iter_fit
         loss = None
-        for itr in range(1, n_iter + 1):
-            task_idx = self._sample_task_indices()
-            self.optimizer.zero_grad()
-            loss = self.get_neg_elbo(task_idx)          # also fills .grad of the posterior parameters
-            self.optimizer.step()
-            self.lr_scheduler.step()
+        itr = 0
+        while itr < n_iter:
+            nxt = 1 if itr == 0 else min(n_iter, (itr // log_period + 1) * log_period)
+            loss = self.run_steps(nxt - itr)
+            itr = nxt
             if itr == 1 or itr % log_period == 0:
                 self._failures.check()
                 duration = time.time() - t
@@ -134,6 +134,92 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
         self._failures.check()
         self.fitted = True
         return loss.item()
+
+    # ------------------------------------------------------------------ device-state / graph-captured steps (diag, Adam)
+    GRAPH_STEPS = 10
+
+    def _device_step(self, K, idx_stream, eps_stream, pre):
+        """One optimisation step whose step-dependent inputs (Adam state, learning rate, task indices, normal draws) are all
+        read from device memory: the same call sequence eager or replayed from a CUDA graph."""
+        st, post = self._state, self.posterior
+        st.prepare(K, self._idx_cur.numel(), idx_stream, self._idx_cur, eps_stream, self._eps_cur)
+        theta, logq = eng.vi_sample(post.loc.detach(), post.scale.detach(), self._eps_cur)
+        logp, g, info = eng.meta_log_prob_and_score(theta, self.engine, self._idx_cur, self._prior_mu, self._prior_sigma,
+                                                    self.prior_factor, pre, self._group)
+        dloc, dscale = eng.vi_grad(post.scale.detach(), self._eps_cur, g, self.prior_factor)
+        post.loc.grad, post.scale.grad = dloc, dscale
+        self.optimizer.step(state=st)
+        self._failures.update(info)
+        return -(logp - self.prior_factor * logq).mean(), info
+
+    def run_steps(self, n):
+        """``n`` iterations of the meta_fit loop body (GPR_meta_vi.py:103-110): sample a batch, -ELBO and its gradient,
+        optimizer step, lr schedule.  Diagonal posterior + Adam: GRAPH_STEPS steps at a time replay from one CUDA graph
+        (task indices from the numpy stream and normal draws from torch's CPU generator are pre-drawn in the reference's
+        order and uploaded per graph); otherwise the reference's eager sequence.  Returns the last loss."""
+        loss = None
+        dev_path = self._state is not None and self.cov_type == 'diag'
+        K = self.GRAPH_STEPS
+        use_graph = dev_path and not self._ragged and self._world == 1 and os.environ.get("PACOH_GRAPH", "1") != "0"
+        S, D = self.svi_batch_size, self.arch.D
+        while n > 0:
+            if not dev_path:
+                loss = self.vi_step(self._sample_task_indices())
+                n -= 1
+                continue
+            lo, hi = eng.shard_bounds(self.task_batch_size, self._rank, self._world)
+            if use_graph and n >= K and self._state.steps > 0 and self._idx_cur is not None and self._idx_cur.numel() == hi - lo:
+                if self._graph is None:
+                    self._idx_stream = torch.zeros(K, hi - lo, dtype=torch.int32, device=self.device)
+                    self._eps_stream = torch.zeros(K, S * D, dtype=torch.float32, device=self.device)
+                    pre = eng.pre_factor(self.task_sizes[:1].repeat(self.task_batch_size))
+                    s0 = self._state.steps
+                    self._graph = eng.StepGraph(lambda: self._device_step(K, self._idx_stream, self._eps_stream, pre), K, self.device)
+                    self._state.steps = s0
+                s0 = self._state.steps
+                rows = np.empty((K, hi - lo), dtype=np.int32)
+                eps = np.empty((K, S * D), dtype=np.float32)
+                for j in range(K):
+                    rows[(s0 + j) % K] = self._sample_task_indices()[lo:hi]
+                    eps[(s0 + j) % K] = torch.empty(S, D).normal_().reshape(-1).numpy()   # Normal.rsample -> _standard_normal
+                self._idx_ring.upload(rows, out=self._idx_stream)
+                self._eps_ring.upload(eps, out=self._eps_stream)
+                loss, self._last_info = self._graph.replay()
+                self._state.steps += K
+                for _ in range(K):
+                    self.lr_scheduler.step()
+                self.optimizer.sync_from(self._state)
+                n -= K
+            else:
+                loss = self.vi_step(self._sample_task_indices())
+                n -= 1
+        return loss
+
+    def vi_step(self, task_idx):
+        """One iteration of the meta_fit loop body on the given batch (GPR_meta_vi.py:106-110): zero_grad, -ELBO and its
+        gradient, optimizer step, lr schedule.  Returns the loss (device scalar)."""
+        if self._state is None or self.cov_type != 'diag':
+            self.optimizer.zero_grad()
+            loss = self.get_neg_elbo(task_idx)
+            self.optimizer.step()
+            self.lr_scheduler.step()
+            return loss
+        S, D = self.svi_batch_size, self.arch.D
+        idx = np.asarray(task_idx, dtype=np.int32)
+        assert idx.shape[0] >= self._world, "task batch smaller than the number of ranks"
+        lo, hi = eng.shard_bounds(idx.shape[0], self._rank, self._world)
+        if self._idx_cur is None or self._idx_cur.numel() != hi - lo:
+            self._idx_cur = torch.empty(hi - lo, dtype=torch.int32, device=self.device)
+            self._eps_cur = torch.empty(S, D, dtype=torch.float32, device=self.device)
+            self._eps_ring = eng.PinnedRing(self.device, dtype=torch.float32)
+            self._graph = None
+        pre = eng.pre_factor(self.task_sizes[idx])
+        istream = self._idx_ring.upload(idx[lo:hi])
+        estream = self._eps_ring.upload(torch.empty(S, D).normal_().reshape(-1).numpy())      # Normal.rsample -> _standard_normal
+        loss, self._last_info = self._device_step(1, istream, estream, pre)
+        self.lr_scheduler.step()
+        self.optimizer.sync_from(self._state)
+        return loss
 
     def _shard(self, task_idx):
         idx = np.asarray(task_idx, dtype=np.int32)
@@ -227,8 +313,10 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
             self.posterior = _FullPosterior(loc.to(self.device), tril.to(self.device), self.arch.entries())
 
     def _setup_optimizer(self, optimizer, lr, lr_decay):
+        self._state, self._graph, self._idx_cur = None, None, None
         if optimizer == 'Adam':
             self.optimizer = eng.PacohAdam(self.posterior.parameters(), lr=lr)
+            self._state = eng.StepState(self.device, lr, lr_decay)
         elif optimizer == 'SGD':
             self.optimizer = torch.optim.SGD(self.posterior.parameters(), lr=lr)
         else:

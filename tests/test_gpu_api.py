@@ -256,3 +256,38 @@ def test_map_module_variants_train(ml, kw):
     l1 = m._loss_and_grad(np.arange(10)).item()
     assert np.isfinite([l0, l1]).all() and l1 < l0
     assert np.isfinite(m.eval_datasets(test)).all()
+
+
+# ---------------------------------------------------------------------------------------------- CUDA-graph replayed steps
+@pytest.mark.parametrize("kind", ["svgd", "vi"])
+def test_graph_replayed_steps_equal_eager_steps(ml, monkeypatch, kind):
+    """run_steps replays GRAPH_STEPS steps per CUDA graph (device-side step state, pre-uploaded index / normal-draw
+    streams: SURVEY 8(f).2); the result must be BITWISE what the eager step sequence gives, lr decay included."""
+    train = orc.sinusoid_tasks(20, 5, seed=26)
+
+    def make():
+        if kind == "svgd":
+            return ml.GPRegressionMetaLearnedSVGD(train, num_particles=10, lr=2e-3, lr_decay=0.5, random_seed=30)
+        return ml.GPRegressionMetaLearnedVI(train, svi_batch_size=8, lr=2e-3, lr_decay=0.5, random_seed=30)
+
+    def params(m):
+        return m.particles if kind == "svgd" else torch.cat([m.posterior.loc.detach(), m.posterior.scale.detach()])
+
+    monkeypatch.setenv("PACOH_GRAPH", "0")
+    a = make()
+    a.run_steps(37)
+    assert a._graph is None
+    monkeypatch.setenv("PACOH_GRAPH", "1")
+    b = make()
+    b.run_steps(1)
+    b.run_steps(36)                      # 1 eager, (1 more eager to reach an even count for svgd) then graphs + eager remainder
+    assert b._graph is not None
+    assert torch.equal(params(a), params(b))
+    assert a._state.steps == b._state.steps == 37
+    st = b.optimizer.state[next(iter(b.optimizer.state))]
+    assert st["step"] == 37
+    torch.manual_seed(7)                                       # VI draws its normals from the (shared) global CPU generator
+    a.meta_fit(verbose=False, log_period=10, n_iter=12)        # meta_fit goes through the same path and stays in sync
+    torch.manual_seed(7)
+    b.meta_fit(verbose=False, log_period=10, n_iter=12)
+    assert torch.equal(params(a), params(b))

@@ -113,6 +113,37 @@ int pacoh_gp_forward(const pacoh_arch_t* arch, int32_t P, int32_t npts, const fl
                      float* mean, float* feat, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Eval-mode exact GP posterior for every parameter vector and a BATCH of test tasks, everything in normalised space
+ * (get_pred_dist: GPR_meta_svgd.py:203-212, GPR_meta_vi.py:229-252, GPR_meta_mll.py:174-183 -> gpytorch ExactGP.eval +
+ * likelihood; abstract.py:134-163):
+ *
+ *   mu[p,t,j]  = m_p(x*_j) + K*c Kt^-1 (y_c - m_p(X_c))            var[p,t,j] = diag(K** - K*c Kt^-1 Kc*) + sigma_p^2
+ *   joint_ll[p,t] = log N(y*_t | mu, Sigma* incl. noise)  with the FULL n* x n* predictive covariance, computed as
+ *                   log N([y_c; y*]) - log N(y_c) with the batched marginal-likelihood kernels (no n* x n* factorisation)
+ *
+ *   x_c (Tt, nc_max, d), y_c (Tt, nc_max), n_c (Tt) int32 or NULL (all nc_max): context sets, zero padded;  nc_max <= 128
+ *   x_s (Tt, ns_max, d), n_s (Tt) int32 or NULL, y_s (Tt, ns_max) or NULL: test inputs / targets (targets only for joint_ll)
+ *   mu, var (P, Tt, ns_max);  cov (P, Tt, ns_max, ns_max) or NULL (full predictive covariance incl. noise, on request);
+ *   joint_ll (P, Tt) or NULL;  info (P, Tt) int32 or NULL (jitter level used / -1, as for the MLL)
+ */
+int64_t pacoh_gp_posterior_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t Tt, int32_t nc_max, int32_t ns_max,
+                                           int32_t want_cov);
+int pacoh_gp_posterior(const pacoh_arch_t* arch, int32_t P, int32_t Tt, int32_t nc_max, int32_t ns_max, const float* theta,
+                       const float* x_c, const float* y_c, const int32_t* n_c, const float* x_s, const int32_t* n_s,
+                       const float* y_s, float* mu, float* var, float* cov, float* joint_ll, int32_t* info, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/*
+ * Evaluation metrics of the equally weighted mixture over the P parameter vectors, one row per test task
+ * (abstract.py:157-161, 260-272; models.py:90-126):  out (Tt, 3) = [ avg test log-likelihood, RMSE, calibration error ]
+ *   ll    = ( logsumexp_p joint_ll[p,t] - log P - n* log y_std ) / n*          (NaN when joint_ll == NULL)
+ *   rmse  = y_std sqrt( mean_j (mean_p mu[p,t,j] - y_s[t,j])^2 )               (y_s: NORMALISED targets)
+ *   calib = sqrt( mean_k ( mean_j [ mean_p Phi((y_j - mu_pj)/sd_pj) <= c_k ] - c_k )^2 ),  c = linspace(0.05, 0.95, 20)
+ */
+int pacoh_pred_metrics(int32_t P, int32_t Tt, int32_t ns_max, const float* mu, const float* var, const int32_t* n_s,
+                       const float* y_s, const float* joint_ll, float y_std, float* out, void* stream);
+
+/*
  * Hyper-prior log-density + combination (RandomGPMeta.log_prob, random_gp.py:179-180,221-222;
  * CatDist.log_prob, models.py:159-181):
  *

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpacoh_b200.so")
-SOURCES = ["capi.cu", "mlp.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_generic.cu", "gp_mll.cu", "gp_tc.cu", "gp_big.cu", "finalize.cu", "svgd.cu"]
+SOURCES = ["capi.cu", "mlp.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "mlp_generic.cu", "gp_mll.cu", "gp_tc.cu", "gp_big.cu", "gp_post.cu", "finalize.cu", "svgd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

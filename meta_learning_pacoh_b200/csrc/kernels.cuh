@@ -40,6 +40,7 @@ struct GpArgs {
   int mean_kind, covar_kind, has_oscale;
   float noise_floor;
   int off_ls, off_noise, off_oscale, off_const_mean;
+  int values_only;        // 1: only mll / info are needed (predictive path): the large-n path then stops after the factorisation
 };
 constexpr int kMaxGpN = 128;   // register kernel: n <= 64; tensor-memory kernel: 32 < n <= 128 (feature dim <= 4)
 constexpr int kMaxBigN = 4096; // blocked tensor-core Cholesky path (gp_big.cu): 64 < n <= 4096, feature dim <= 4
@@ -53,6 +54,7 @@ int launch_gp_mll_big(const GpArgs& a, void* ws, size_t ws_bytes, cudaStream_t s
 void gp_big_layout_debug(int n, long long matrices, long long* out);
 bool gp_use_big(int n, int F);   // capi.cu: which path a (n, F) problem takes
 
+// ---- eval-mode posterior + evaluation metrics (gp_post.cu): C-ABI entry points only, see include/pacoh_b200.h
 // ---- reductions / elementwise (finalize.cu) ------------------------------------------------------------
 int launch_reduce_partials(const float* partial, int chunks, int P, int total, float* dtheta, int D, int dst_off,
                            cudaStream_t st);

@@ -581,7 +581,11 @@ int mlp_tc_bwd_slots(int P, int nets, int Q, int* grid_out, int* per_cta_out) {
   if (waves < 1) waves = 1;
   const long long ctas = (long long)sms * waves;
   long long per = (total + ctas - 1) / ctas;
-  if (per < 6) per = 6;          // at least two tiles per warpgroup: below that the fixed per-CTA cost dominates
+  // at least two tiles per warpgroup when there is enough work to fill the machine anyway (below that the fixed per-CTA cost
+  // dominates the throughput); small launches (configs #1 - #3: a few dozen tiles) spread over as many SMs as they have
+  // tiles instead -- their cost is latency, and six (net, particle) segments in a row on one SM cost ~100 us
+  if (per < 6 && total >= 6LL * sms) per = 6;
+  if (per < 1) per = 1;
   const int grid = (int)((total + per - 1) / per);
   int slots = 1;
   for (long long pn = 0; pn < (long long)nets * P; ++pn) {

@@ -521,49 +521,126 @@ def gp_forward(arch: GPArch, theta, x):
     return mean, feat
 
 
-def gp_hypers(arch: GPArch, theta):
-    """lengthscale (P, F), noise variance (P,), outputscale (P,) from the raw entries (random_gp.py:69-73)."""
-    ent = arch.entries()
-    sp = torch.nn.functional.softplus
-    a, b = ent["lengthscale_raw"]
-    ls = sp(theta[:, a:b])
-    noise = sp(theta[:, ent["noise_raw"][0]]) + arch.noise_floor
-    osc = sp(theta[:, ent["outputscale_raw"][0]]) if arch.outputscale else torch.ones_like(noise)
-    return ls, noise, osc
+class PosteriorBatch:
+    """Eval-mode posterior of P parameter vectors on a batch of test tasks (pacoh_gp_posterior), normalised space.
+    ``mu`` / ``var`` (P, Tt, ns_max) device tensors (var includes the observation noise), ``n_s`` per-task test sizes,
+    ``joint_ll`` (P, Tt) when targets were given, ``cov`` (P, Tt, ns_max, ns_max) on request, ``info`` (P, Tt)."""
+
+    def __init__(self, mu, var, n_s, joint_ll, cov, info, ys_dev):
+        self.mu, self.var, self.n_s, self.joint_ll, self.cov, self.info, self.ys_dev = mu, var, n_s, joint_ll, cov, info, ys_dev
 
 
-def gp_posterior(arch: GPArch, theta, x_context, y_context, x_test):
-    """Eval-mode exact GP posterior for every parameter vector (gpytorch ExactGP.eval + likelihood, reached from
-    get_pred_dist, GPR_meta_svgd.py:203-212 / GPR_meta_vi.py:229-252 / GPR_meta_mll.py:174-183):
-        mu* = m(X*) + K*^T Kt^-1 (y - m(X)),  Sigma* = K** - K*^T Kt^-1 K* + sigma^2 I     (normalised space)
-    The nets run in the CUDA kernels (pacoh_gp_forward); the n_c x n_c / n* x n* dense algebra uses torch.linalg on
-    the device -- SURVEY 8(f).1 ranks a dedicated posterior kernel as the next row.
-    Returns mean (P, n*), covariance (P, n*, n*) including observation noise."""
-    nc = x_context.shape[0]
-    xa = torch.cat([x_context, x_test], 0)
-    mean, feat = gp_forward(arch, theta, xa)
-    ls, noise, osc = gp_hypers(arch, theta)
-    u = feat / ls.unsqueeze(1)
-    uc, us = u[:, :nc], u[:, nc:]
+_post_ws = {}
 
-    def gram(a, b):
-        d2 = (a.unsqueeze(2) - b.unsqueeze(1)).pow(2).sum(-1)
-        return osc.view(-1, 1, 1) * torch.exp(-0.5 * d2)
 
-    P = theta.shape[0]
-    eye_c = torch.eye(nc, device=theta.device, dtype=torch.float32)
-    eye_s = torch.eye(x_test.shape[0], device=theta.device, dtype=torch.float32)
-    Kcc = gram(uc, uc) + noise.view(P, 1, 1) * eye_c
-    Kcs, Kss = gram(uc, us), gram(us, us)
-    L, info = torch.linalg.cholesky_ex(Kcc)
-    if int(info.max().item()) > 0:
-        raise NotPSDError("context kernel matrix is not positive definite")
-    r = (y_context.view(1, nc) - mean[:, :nc]).unsqueeze(-1)
-    alpha = torch.cholesky_solve(r, L)
-    mu = mean[:, nc:] + (Kcs.transpose(1, 2) @ alpha).squeeze(-1)
-    V = torch.linalg.solve_triangular(L, Kcs, upper=False)
-    cov = Kss - V.transpose(1, 2) @ V + noise.view(P, 1, 1) * eye_s
-    return mu, cov
+def gp_posterior_batch(arch: GPArch, theta, contexts, tests, targets=None, want_cov=False):
+    """Exact GP posterior for every row of ``theta`` (P, D) on Tt test tasks at once (get_pred_dist of the reference, per
+    task and per particle: GPR_meta_svgd.py:203-212, GPR_meta_vi.py:229-252, GPR_meta_mll.py:174-183).
+
+    contexts: list of (x_c (n_c, d), y_c (n_c,)) normalised float arrays / tensors; tests: list of x* (n*, d);
+    targets: optional list of normalised y* (n*,) -> joint log-likelihoods.  All algebra runs in the CUDA kernels of
+    csrc/gp_post.cu (no torch.linalg): returns a PosteriorBatch."""
+    theta = _f32c(theta.detach().contiguous(), theta.device)
+    dev = theta.device
+    P, D = theta.shape
+    assert D == arch.D
+    Tt, d = len(contexts), arch.input_dim
+    assert len(tests) == Tt and (targets is None or len(targets) == Tt)
+    as_np = lambda v: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)).astype(np.float32)   # noqa: E731
+    nc = np.asarray([len(c[0]) for c in contexts], dtype=np.int32)
+    ns = np.asarray([len(x) for x in tests], dtype=np.int32)
+    nc_max, ns_max = int(nc.max()), int(ns.max())
+    xc = np.zeros((Tt, nc_max, d), np.float32); yc = np.zeros((Tt, nc_max), np.float32)
+    xs = np.zeros((Tt, ns_max, d), np.float32); ys = np.zeros((Tt, ns_max), np.float32)
+    for t in range(Tt):
+        xc[t, :nc[t]] = as_np(contexts[t][0]).reshape(nc[t], d)
+        yc[t, :nc[t]] = as_np(contexts[t][1]).reshape(nc[t])
+        xs[t, :ns[t]] = as_np(tests[t]).reshape(ns[t], d)
+        if targets is not None:
+            ys[t, :ns[t]] = as_np(targets[t]).reshape(ns[t])
+    up = lambda a_: torch.from_numpy(a_).to(dev)   # noqa: E731
+    xc_d, yc_d, xs_d, nc_d, ns_d = up(xc), up(yc), up(xs), up(nc), up(ns)
+    ys_d = up(ys) if targets is not None else None
+    a = arch.c_struct()
+    nbytes = check(lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), P, Tt, nc_max, ns_max, 1 if want_cov else 0))
+    key = (dev, )
+    if key not in _post_ws or _post_ws[key].numel() < nbytes:
+        _post_ws[key] = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+    ws = _post_ws[key]
+    mu = torch.empty(P, Tt, ns_max, dtype=torch.float32, device=dev)
+    var = torch.empty_like(mu)
+    cov = torch.empty(P, Tt, ns_max, ns_max, dtype=torch.float32, device=dev) if want_cov else None
+    jll = torch.empty(P, Tt, dtype=torch.float32, device=dev) if targets is not None else None
+    info = torch.empty(P, Tt, dtype=torch.int32, device=dev)
+    check(lib.pacoh_gp_posterior(ctypes.byref(a), P, Tt, nc_max, ns_max, _ptr(theta), _ptr(xc_d), _ptr(yc_d), _ptr(nc_d), _ptr(xs_d),
+                                 _ptr(ns_d), _ptr(ys_d), _ptr(mu), _ptr(var), _ptr(cov), _ptr(jll), _ptr(info), _ptr(ws), ws.numel(), _stream()))
+    return PosteriorBatch(mu, var, ns_d, jll, cov, info, ys_d)
+
+
+def pred_metrics(post: PosteriorBatch, y_std):
+    """(Tt, 3) tensor [avg test log-likelihood, RMSE, calibration error] per test task of the equally weighted mixture over
+    the parameter vectors (abstract.py:157-161, 260-272; models.py:90-126): pacoh_pred_metrics."""
+    P, Tt, ns_max = post.mu.shape
+    assert post.ys_dev is not None, "metrics need the test targets"
+    out = torch.empty(Tt, 3, dtype=torch.float32, device=post.mu.device)
+    check(lib.pacoh_pred_metrics(P, Tt, ns_max, _ptr(post.mu), _ptr(post.var), _ptr(post.n_s), _ptr(post.ys_dev), _ptr(post.joint_ll),
+                                 float(y_std), _ptr(out), _stream()))
+    return out
+
+
+class GPPredictive(torch.distributions.Distribution):
+    """The normalised-space predictive distribution of one test task: what gpytorch's MultivariateNormal is to the
+    reference's get_pred_dist (batch = parameter vectors, event = test points).  ``mean`` / ``variance`` / ``stddev`` come
+    from the posterior kernel; ``log_prob(y)`` is the JOINT density with the full predictive covariance, evaluated on the
+    device through the marginal-likelihood kernels; ``covariance_matrix`` is built on first access; ``cdf`` / ``icdf`` are
+    the marginal Normal ones.  ``squeeze=True`` drops the batch dimension (PACOH-MAP / VI 'MAP' mode: one parameter vector)."""
+    arg_constraints = {}
+    has_rsample = False
+
+    def __init__(self, arch, theta, context, x_test, squeeze=False):
+        self._arch, self._theta, self._context, self._x = arch, theta, context, x_test
+        post = gp_posterior_batch(arch, theta, [context], [x_test])
+        if int(post.info.min().item()) < 0:
+            raise NotPSDError("context kernel matrix is not positive definite")
+        self._squeeze = squeeze
+        self._mean, self._var = post.mu[:, 0].cpu(), post.var[:, 0].cpu()
+        self._cov = None
+        P, ns = self._mean.shape
+        super().__init__(batch_shape=torch.Size([]) if squeeze else torch.Size([P]), event_shape=torch.Size([ns]), validate_args=False)
+
+    def _sq(self, v):
+        return v[0] if self._squeeze else v
+
+    @property
+    def mean(self):
+        return self._sq(self._mean)
+
+    loc = mean
+
+    @property
+    def variance(self):
+        return self._sq(self._var)
+
+    @property
+    def stddev(self):
+        return self._sq(self._var.sqrt())
+
+    @property
+    def covariance_matrix(self):
+        if self._cov is None:
+            self._cov = gp_posterior_batch(self._arch, self._theta, [self._context], [self._x], want_cov=True).cov[:, 0].cpu()
+        return self._sq(self._cov)
+
+    def log_prob(self, value):
+        value = torch.as_tensor(value, dtype=torch.float32).reshape(-1)
+        post = gp_posterior_batch(self._arch, self._theta, [self._context], [self._x], targets=[value])
+        return self._sq(post.joint_ll[:, 0].cpu())
+
+    def cdf(self, value):
+        return torch.distributions.Normal(self.mean, self.stddev).cdf(value)
+
+    def icdf(self, value):
+        return torch.distributions.Normal(self.mean, self.stddev).icdf(value)
 
 
 class PacohAdam(torch.optim.Optimizer):

@@ -181,21 +181,14 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
     # ------------------------------------------------------------------ prediction
     def predict(self, context_x, context_y, test_x, return_density=False):
         """Posterior inference on the context set, predictive distribution at test_x -- GPR_meta_mll.py:149-190."""
-        mu, cov = self._predict_normalised(context_x, context_y, test_x)
-        base = torch.distributions.MultivariateNormal(mu[0].cpu(), covariance_matrix=cov[0].cpu())
+        base = self._predictive(context_x, context_y, test_x, squeeze=True)
         pred = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
         if return_density:
             return pred
         return pred.mean.numpy(), pred.stddev.numpy()
 
-    def _predict_normalised(self, context_x, context_y, test_x):
-        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
-        test_x = _handle_input_dimensionality(test_x)
-        assert test_x.shape[1] == context_x.shape[1]
-        xc, yc = self._prepare_data_per_task(context_x, context_y)
-        xs = torch.from_numpy(self._normalize_data(X=test_x, Y=None)).float().to(self.device)
-        with torch.no_grad():
-            return eng.gp_posterior(self.arch, self._pack(), xc, yc, xs)
+    def _predict_params(self):
+        return self._pack()
 
     # ------------------------------------------------------------------ checkpointing (GPR_meta_mll.py:192-205)
     def _model_state(self):

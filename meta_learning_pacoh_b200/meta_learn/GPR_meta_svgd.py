@@ -269,22 +269,16 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
     def predict(self, context_x, context_y, test_x, return_density=False):
         """Posterior inference on (context_x, context_y), predictive mixture over particles at test_x --
         GPR_meta_svgd.py:123-159."""
-        mu, cov = self._predict_normalised(context_x, context_y, test_x)
-        base = torch.distributions.MultivariateNormal(mu.cpu(), covariance_matrix=cov.cpu())
+        self._failures.check()
+        base = self._predictive(context_x, context_y, test_x)
         pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
         pred_dist = EqualWeightedMixtureDist(pred_dist, batched=True)
         if return_density:
             return pred_dist
         return pred_dist.mean.numpy(), pred_dist.stddev.numpy()
 
-    def _predict_normalised(self, context_x, context_y, test_x):
-        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
-        test_x = _handle_input_dimensionality(test_x)
-        assert test_x.shape[1] == context_x.shape[1]
-        xc, yc = self._prepare_data_per_task(context_x, context_y)
-        xs = torch.from_numpy(self._normalize_data(X=test_x, Y=None)).float().to(self.device)
-        with torch.no_grad():
-            return eng.gp_posterior(self.arch, self.particles, xc, yc, xs)
+    def _predict_params(self):
+        return self.particles
 
     # ------------------------------------------------------------------ setup
     def _setup_model_inference(self, mean_module_str, covar_module_str, mean_nn_layers, kernel_nn_layers,

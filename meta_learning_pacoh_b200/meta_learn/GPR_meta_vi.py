@@ -262,14 +262,11 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
     def predict(self, context_x, context_y, test_x, n_posterior_samples=100, mode='Bayes', return_density=False):
         """Predictive distribution p(y | test_x, context) -- GPR_meta_vi.py:130-174."""
         assert mode in ['bayes', 'Bayes', 'MAP', 'map']
-        mu, cov = self._predict_normalised(context_x, context_y, test_x, n_posterior_samples=n_posterior_samples, mode=mode)
-        if mode in ('Bayes', 'bayes'):
-            base = torch.distributions.MultivariateNormal(mu.cpu(), covariance_matrix=cov.cpu())
-            pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
+        bayes = mode in ('Bayes', 'bayes')
+        base = self._predictive(context_x, context_y, test_x, squeeze=not bayes, n_posterior_samples=n_posterior_samples, mode=mode)
+        pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
+        if bayes:
             pred_dist = EqualWeightedMixtureDist(pred_dist, batched=True)
-        else:
-            base = torch.distributions.MultivariateNormal(mu[0].cpu(), covariance_matrix=cov[0].cpu())   # GPR_meta_vi.py:252
-            pred_dist = AffineTransformedDistribution(base, normalization_mean=self.y_mean, normalization_std=self.y_std)
         if return_density:
             return pred_dist
         return pred_dist.mean.numpy(), pred_dist.stddev.numpy()
@@ -283,18 +280,16 @@ class GPRegressionMetaLearnedVI(RegressionModelMetaLearned):
             eps = torch.empty(n, self.arch.D).normal_().to(self.device)
             return (self.posterior.loc + eps @ torch.tril(self.posterior.tril_cov).T).contiguous()
 
-    def _predict_normalised(self, context_x, context_y, test_x, n_posterior_samples=100, mode='Bayes'):
-        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
-        test_x = _handle_input_dimensionality(test_x)
-        assert test_x.shape[1] == context_x.shape[1]
-        xc, yc = self._prepare_data_per_task(context_x, context_y)
-        xs = torch.from_numpy(self._normalize_data(X=test_x, Y=None)).float().to(self.device)
+    def _predict_params(self, n_posterior_samples=100, mode='Bayes'):
+        """'Bayes': n_posterior_samples draws from the variational posterior (GPR_meta_vi.py:229-239); 'MAP': its mode (:241-252)."""
+        assert mode in ['bayes', 'Bayes', 'MAP', 'map']
         with torch.no_grad():
             if mode in ('Bayes', 'bayes'):
-                params = self._sample_posterior(n_posterior_samples)
-            else:
-                params = self.posterior.mode.view(1, -1).contiguous()
-            return eng.gp_posterior(self.arch, params.contiguous(), xc, yc, xs)
+                return self._sample_posterior(n_posterior_samples).contiguous()
+            return self.posterior.mode.view(1, -1).contiguous()
+
+    def _eval_per_task(self, n_posterior_samples=100, mode='Bayes'):
+        return mode in ('Bayes', 'bayes')      # the reference draws fresh posterior samples for every test task (predict per task)
 
     # ------------------------------------------------------------------ setup
     def _setup_model_inference(self, mean_module_str, covar_module_str, mean_nn_layers, kernel_nn_layers, cov_type):

@@ -1,9 +1,10 @@
 """Base class of the meta-learners: seeding, normalisation, per-task tensors and the evaluation API
 (eval / eval_datasets / confidence_intervals), call-compatible with meta_learn/abstract.py:117-272 of the reference.
 
-The evaluation metrics are computed on the device from the batched predictive mean / covariance the subclasses
-return in ``_predict_normalised`` -- the reference builds torch.distributions objects on the CPU and the same
-numbers fall out of them (abstract.py:157-161, models.py:15-43, 90-126).
+The evaluation path runs in the CUDA kernels of csrc/gp_post.cu: one batched posterior call for all test tasks
+(engine.gp_posterior_batch -> pacoh_gp_posterior) and one metrics kernel (pacoh_pred_metrics); the reference builds
+gpytorch / torch.distributions objects per task on the CPU and the same numbers fall out of them (abstract.py:157-161,
+models.py:15-43, 90-126).
 """
 import math
 import os
@@ -45,19 +46,52 @@ class RegressionModelMetaLearned:
 
     def eval(self, context_x, context_y, test_x, test_y, flatten_y=True, **kwargs):
         """(avg test log-likelihood, rmse, calibration error) on one task -- abstract.py:134-163."""
-        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
-        test_x, test_y = _handle_input_dimensionality(test_x, test_y)
         assert flatten_y, "only scalar targets are supported"
-        mu, cov = self._predict_normalised(context_x, context_y, test_x, **kwargs)    # (P, n*), (P, n*, n*)
-        y = torch.from_numpy(test_y).float().flatten().to(self.device)
-        return self._metrics(mu, cov, y)
+        return tuple(float(v) for v in self._eval_batch([(context_x, context_y, test_x, test_y)], **kwargs)[0])
 
     def eval_datasets(self, test_tuples, flatten_y=True, **kwargs):
-        """Average of eval() over test tasks -- abstract.py:165-181."""
-        assert all(len(t) == 4 for t in test_tuples)
-        res = [self.eval(*t, flatten_y=flatten_y, **kwargs) for t in test_tuples]
-        ll, rmse, cal = zip(*res)
-        return np.mean(ll), np.mean(rmse), np.mean(cal)
+        """Average of eval() over test tasks -- abstract.py:165-181.  All test tasks go through ONE batched posterior call
+        (the reference loops over them) unless the learner draws fresh parameter samples per task."""
+        assert all(len(t) == 4 for t in test_tuples) and flatten_y
+        if self._eval_per_task(**kwargs):
+            res = np.concatenate([self._eval_batch([t], **kwargs) for t in test_tuples], axis=0)
+        else:
+            res = self._eval_batch(list(test_tuples), **kwargs)
+        return float(np.mean(res[:, 0])), float(np.mean(res[:, 1])), float(np.mean(res[:, 2]))
+
+    def _eval_per_task(self, **kwargs):
+        return False
+
+    def _eval_batch(self, tuples, **kwargs):
+        """(len(tuples), 3) array of [ll, rmse, calib]: posterior + metrics kernels (csrc/gp_post.cu)."""
+        ctxs, xss, yns = [], [], []
+        for cx, cy, tx, ty in tuples:
+            cx, cy = _handle_input_dimensionality(cx, cy)
+            tx, ty = _handle_input_dimensionality(tx, ty)
+            assert tx.shape[1] == cx.shape[1]
+            cxn, cyn = self._normalize_data(cx, cy)
+            ctxs.append((cxn, cyn.flatten()))
+            xss.append(self._normalize_data(X=tx, Y=None))
+            yns.append(((ty - self.y_mean[None, :]) / self.y_std[None, :]).flatten())
+        with torch.no_grad():
+            post = eng.gp_posterior_batch(self.arch, self._predict_params(**kwargs), ctxs, xss, targets=yns)
+            out = eng.pred_metrics(post, float(self.y_std[0]))
+            if int(post.info.min().item()) < 0:
+                raise eng.NotPSDError("a context / predictive kernel matrix is not positive definite")
+        return out.cpu().numpy().astype(np.float64)
+
+    def _predict_params(self, **kwargs):
+        """(P, D) parameter vectors the predictive distribution mixes over."""
+        raise NotImplementedError
+
+    def _predictive(self, context_x, context_y, test_x, squeeze=False, **kwargs):
+        """engine.GPPredictive for one task in normalised space."""
+        context_x, context_y = _handle_input_dimensionality(context_x, context_y)
+        test_x = _handle_input_dimensionality(test_x)
+        assert test_x.shape[1] == context_x.shape[1]
+        cxn, cyn = self._normalize_data(context_x, context_y)
+        with torch.no_grad():
+            return eng.GPPredictive(self.arch, self._predict_params(**kwargs), (cxn, cyn.flatten()), self._normalize_data(X=test_x, Y=None), squeeze=squeeze)
 
     def confidence_intervals(self, context_x, context_y, test_x, confidence=0.9, **kwargs):
         """(ucb, lcb) of the marginal predictive distribution -- abstract.py:183-204."""
@@ -68,29 +102,6 @@ class RegressionModelMetaLearned:
         ucb = pred_dist.icdf(torch.ones(shape) * (1 - alpha))
         lcb = pred_dist.icdf(torch.ones(shape) * alpha)
         return ucb, lcb
-
-    # ------------------------------------------------------------------ metrics on device
-    def _metrics(self, mu, cov, y):
-        P, ns = mu.shape
-        y_mean, y_std = float(self.y_mean[0]), float(self.y_std[0])
-        yn = (y - y_mean) / y_std
-        L, info = torch.linalg.cholesky_ex(cov)
-        if int(info.max().item()) > 0:
-            raise eng.NotPSDError("predictive covariance is not positive definite")
-        r = (yn.view(1, ns) - mu).unsqueeze(-1)
-        zs = torch.linalg.solve_triangular(L, r, upper=False).squeeze(-1)
-        logdet = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
-        lp = -0.5 * (zs ** 2).sum(-1) - 0.5 * logdet - 0.5 * ns * math.log(2 * math.pi) - ns * math.log(y_std)
-        ll = (torch.logsumexp(lp, 0) - math.log(P)) / ns
-        m = mu * y_std + y_mean
-        s = torch.sqrt(torch.diagonal(cov, dim1=-2, dim2=-1)) * y_std
-        rmse = torch.sqrt(torch.mean((m.mean(0) - y) ** 2))
-        cdf = (0.5 * (1 + torch.erf((y.view(1, ns) - m) / (s * math.sqrt(2.0))))).mean(0)
-        conf = torch.linspace(0.05, 0.95, 20, device=mu.device)
-        emp = (cdf[:, None] <= conf).sum(0).float() / ns
-        calib = torch.sqrt(torch.mean((emp - conf) ** 2))
-        out = torch.stack([ll, rmse, calib]).cpu()
-        return out[0].item(), out[1].item(), out[2].item()
 
     # ------------------------------------------------------------------ data handling (abstract.py:212-258)
     def _compute_normalization_stats(self, meta_train_tuples):
@@ -165,5 +176,4 @@ class RegressionModelMetaLearned:
     def _vectorize_pred_dist(self, pred_dist):
         raise NotImplementedError
 
-    def _predict_normalised(self, context_x, context_y, test_x, **kwargs):
-        raise NotImplementedError
+

@@ -9,9 +9,9 @@
 //   LL    = log N(y* | mu*, Sigma*)  (the full n* x n* covariance)
 //
 // How it is computed here (normalised matrix Khat = Kt / tot, tot = s + sigma^2, rho = s / tot, as in the MLL kernels):
-//   * one CTA per (parameter vector, test task): Khat_cc (n_c <= 128) is factorised in shared memory (potrf + trtri,
-//     chol128.cuh), alphahat = Khat^-1 r and Khat^-1 = U U^T follow; then one thread per test point:
-//        mu_j = m_j + khat_j . alphahat          var_j = tot (1 - khat_j^T Khat^-1 khat_j)       khat_j = rho k(x_j, X_c)
+//   * one CTA per (parameter vector, test task): Khat_cc = L L^T (n_c <= 128) is factorised in shared memory (potrf + trtri,
+//     chol128.cuh), v = L^-1 r; then one thread per test point, forward substitution w_j = L^-1 khat_j:
+//        mu_j = m_j + w_j . v                     var_j = tot (1 - w_j . w_j)                     khat_j = rho k(x_j, X_c)
 //   * the joint log-likelihood needs no n* x n* factorisation of Sigma*: by the chain rule of Gaussians
 //        log N(y* | mu*, Sigma*) = log N([y_c; y*] | joint prior) - log N(y_c | prior)
 //     i.e. two calls of the batched marginal-log-likelihood kernels (values only) on the packed [context; test] point sets,
@@ -52,7 +52,7 @@ struct PostArgs {
   const float* mean; const float* feat;    // (P, Tt * nj_max), (P, Tt * nj_max, F) from the nets, or nullptr
   float* mu; float* var;                   // (P, Tt, ns_max)
   int* info;                               // (P, Tt) or nullptr
-  float* kcs; float* zcs;                  // (P, Tt, nc_max, ns_max) scratch for the full covariance, or nullptr
+  float* kcs;                              // (P, Tt, nc_max, ns_max) scratch for the full covariance: W = L^-1 Khat_c*, or nullptr
   float* cov;                              // (P, Tt, ns_max, ns_max) or nullptr
 };
 
@@ -135,27 +135,16 @@ __global__ void __launch_bounds__(256, 1) gp_post_kernel(PostArgs a) {
     if (ok) { status = lvl; break; }
   }
   if (a.info != nullptr && tid == 0) a.info[(size_t)p * a.Tt + t] = status;
-  // v = L^-1 r = U^T r ; alphahat = U v ; Khat^-1 = U U^T (only the leading nc x nc block is needed)
+  // v = L^-1 r = U^T r
   if (tid < NBP) {
     float v = 0.0f;
     for (int i = 0; i <= tid && i < nc; ++i) v = fmaf(X[i * LDT + tid], rs[i], v);
     vs[tid] = tid < nc ? v : 0.0f;
   }
   conv_sync();
-  if (tid < NBP) {
-    float al = 0.0f;
-    for (int c = tid; c < nc; ++c) al = fmaf(X[tid * LDT + c], vs[c], al);
-    rs[tid] = tid < nc ? al : 0.0f;                      // rs now holds alphahat
-  }
-  if (r < nc) {
-    for (int c = h; c < nc; c += 2) {
-      float s = 0.0f;
-      for (int m = max(r, c); m < nc; ++m) s = fmaf(X[r * LDT + m], X[c * LDT + m], s);
-      T[r * LDT + c] = s;
-    }
-  }
-  conv_sync();
-  // ---- test points, 128 at a time (threads 0..127); X is free: it holds the khat vectors, [i][thread]
+  // ---- test points, 128 at a time (threads 0..127).  X is free now: it holds the vectors khat_j -> w_j = L^-1 khat_j
+  //      ([i][thread], forward substitution in place -- the backward-stable form; k^T Khat^-1 k through an explicit inverse
+  //      loses the 1e-4 bar on the variance where 1 - w.w cancels):  mu_j = m_j + w_j . v,  var_j = tot (1 - w_j . w_j)
   float* ks = X;
   const float lg2rho = log2f(rho);
   const bool failed = status < 0;
@@ -165,19 +154,18 @@ __global__ void __launch_bounds__(256, 1) gp_post_kernel(PostArgs a) {
       float4 uj;
       float mj;
       point(nc + j, uj, mj);
-      float mean = 0.0f;
-      for (int i = 0; i < nc; ++i) {
-        const float ki = khat_p(uj, ucs[i], lg2rho);
-        ks[i * NBP + tid] = ki;
-        mean = fmaf(ki, rs[i], mean);
-      }
-      float q = 0.0f;
+      for (int i = 0; i < nc; ++i) ks[i * NBP + tid] = khat_p(uj, ucs[i], lg2rho);
+      float mean = 0.0f, q = 0.0f;
       const size_t so = (((size_t)p * a.Tt + t) * a.nc_max) * a.ns_max + j;
       for (int i = 0; i < nc; ++i) {
-        float z = 0.0f;
-        for (int c = 0; c < nc; ++c) z = fmaf(T[i * LDT + c], ks[c * NBP + tid], z);
-        q = fmaf(ks[i * NBP + tid], z, q);
-        if (a.zcs != nullptr) { a.zcs[so + (size_t)i * a.ns_max] = z; a.kcs[so + (size_t)i * a.ns_max] = ks[i * NBP + tid]; }
+        float sacc = ks[i * NBP + tid];
+        const float* Li = T + i * LDT;
+        for (int m = 0; m < i; ++m) sacc = fmaf(-Li[m], ks[m * NBP + tid], sacc);
+        const float w = sacc / Li[i];
+        ks[i * NBP + tid] = w;
+        mean = fmaf(w, vs[i], mean);
+        q = fmaf(w, w, q);
+        if (a.kcs != nullptr) a.kcs[so + (size_t)i * a.ns_max] = w;
       }
       const size_t o = ((size_t)p * a.Tt + t) * a.ns_max + j;
       a.mu[o] = failed ? CUDART_NAN_F : mj + mean;
@@ -194,7 +182,7 @@ __global__ void __launch_bounds__(256, 1) gp_post_kernel(PostArgs a) {
 }
 
 // Full predictive covariance (only on request: predict(return_density=True).covariance_matrix):
-//   Sigma*_jk = tot (rho k(x_j, x_k) + (1 - rho) delta_jk - khat_j^T Khat^-1 khat_k).   grid (ceil(ns/16), ceil(ns/16), P * Tt)
+//   Sigma*_jk = tot (rho k(x_j, x_k) + (1 - rho) delta_jk - w_j . w_k),  w = L^-1 khat.   grid (ceil(ns/16), ceil(ns/16), P * Tt)
 __global__ void gp_post_cov_kernel(PostArgs a) {
   const int pt = blockIdx.z, p = pt / a.Tt, t = pt - p * a.Tt;
   const int nc = a.ncv[t], ns = a.njv[t] - nc;
@@ -218,7 +206,7 @@ __global__ void gp_post_cov_kernel(PostArgs a) {
   }
   float s = 0.0f;
   const size_t so = ((size_t)pt * a.nc_max) * a.ns_max;
-  for (int i = 0; i < nc; ++i) s = fmaf(a.kcs[so + (size_t)i * a.ns_max + j], a.zcs[so + (size_t)i * a.ns_max + k], s);
+  for (int i = 0; i < nc; ++i) s = fmaf(a.kcs[so + (size_t)i * a.ns_max + j], a.kcs[so + (size_t)i * a.ns_max + k], s);
   *out = tot * ((j == k ? 1.0f : rho * ex2p(-d2)) - s);
 }
 
@@ -289,7 +277,7 @@ struct PostPlan {
   ModelDev m;
   int nj_max;
   bool big;
-  size_t off_xj, off_yj, off_nj, off_nc, off_idx, off_mean, off_feat, off_mllj, off_mllc, off_hyp, off_infoj, off_kcs, off_zcs,
+  size_t off_xj, off_yj, off_nj, off_nc, off_idx, off_mean, off_feat, off_mllj, off_mllc, off_hyp, off_infoj, off_kcs,
       off_fwd, fwd_bytes, off_big, big_bytes, total;     // byte offsets
 };
 
@@ -315,7 +303,6 @@ int post_plan(const pacoh_arch_t* arch, int P, int Tt, int nc_max, int ns_max, b
   pl->off_hyp = take(PT * gp_hyp_stride(m.F) * 4);
   pl->off_infoj = take(PT * 4);
   pl->off_kcs = take(want_cov ? PT * nc_max * ns_max * 4 : 0);
-  pl->off_zcs = take(want_cov ? PT * nc_max * ns_max * 4 : 0);
   const int64_t fb = pacoh_gp_forward_workspace_bytes(arch, P, (int32_t)pts);
   if (fb < 0) return (int)fb;
   pl->fwd_bytes = (size_t)fb;
@@ -372,7 +359,6 @@ extern "C" int pacoh_gp_posterior(const pacoh_arch_t* arch, int32_t P, int32_t T
   a.xj = xj; a.yj = yj; a.ncv = ncv; a.njv = njv; a.nj_max = pl.nj_max; a.nc_max = nc_max; a.ns_max = ns_max;
   a.mean = mean; a.feat = feat; a.mu = mu; a.var = var; a.info = info; a.cov = cov;
   a.kcs = cov != nullptr ? (float*)(ws + pl.off_kcs) : nullptr;
-  a.zcs = cov != nullptr ? (float*)(ws + pl.off_zcs) : nullptr;
   const size_t smem = sizeof(float) * (2 * NBP * LDT + 4 * NBP + 2 * NBP + 64);
   static bool once = false;
   if (!once) { PACOH_CUDA_CHECK(cudaFuncSetAttribute(gp_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }

@@ -39,6 +39,7 @@ class NeuralNetwork(torch.nn.Sequential):
 
 
 class GPRegressionMetaLearned(RegressionModelMetaLearned):
+    NOISE_FLOOR = 1e-3     # gpytorch GaussianLikelihood(noise_constraint=GreaterThan(1e-3)), GPR_meta_mll.py:54-55
 
     def __init__(self, meta_train_data, learning_mode='both', lr_params=1e-3, weight_decay=0.0, feature_dim=2,
                  num_iter_fit=10000, covar_module='NN', mean_module='NN', mean_nn_layers=(32, 32), kernel_nn_layers=(32, 32),
@@ -65,6 +66,7 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
 
         X, Y = self._build_task_dicts(meta_train_data)
         self.engine = eng.MetaMLLEngine(self.arch, X, Y, self.device, task_n=self.task_sizes)
+        self._flatten_parameters()
         self._setup_optimizer(optimizer, lr_params, lr_decay)
         self._idx_ring = eng.PinnedRing(self.device)
         self._failures = eng.FailureFlag(self.device)
@@ -90,17 +92,31 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         assert [n for n, _ in out] == list(self.arch.entries().keys())
         return out
 
-    def _pack(self):
-        return torch.cat([t.detach().reshape(-1) for _, t in self._named_flat()]).view(1, -1).contiguous()
-
-    def _scatter_grad(self, flat_grad):
+    def _flatten_parameters(self):
+        """Make every module parameter a VIEW into one flat (1, D) buffer in the engine's layout (and its gradient a view into
+        a flat gradient buffer): packing the parameters for the kernels is then free and scattering the gradient is one
+        copy, instead of a cat over 15 tensors and 15 clones per step.  The nn.Parameter objects (names, state_dict keys,
+        optimizer groups) are unchanged; in-place updates by the optimizer / load_state_dict keep the views valid."""
+        named = self._named_flat()
+        flat = torch.cat([t.detach().reshape(-1) for _, t in named]).contiguous()
+        self._flat, self._gradflat = flat.view(1, -1), torch.zeros_like(flat)
         learn_kernel = self.learning_mode in ("learn_kernel", "both")
         learn_mean = self.learning_mode in ("learn_mean", "both")
-        for (name, t), (a, b) in zip(self._named_flat(), self.arch.entries().values()):
+        self._grad_views = []
+        for (name, t), (a, b) in zip(named, self.arch.entries().values()):
+            t.data = flat[a:b].view(t.shape)
             trainable = {"mean_nn": learn_mean, "constant_mean": learn_mean, "kernel_nn": learn_kernel,
                          "lengthscale_raw": learn_kernel, "outputscale_raw": learn_kernel, "noise_raw": True}[name.split(".")[0]]
             if trainable:
-                t.grad = flat_grad[a:b].view_as(t).clone()
+                self._grad_views.append((t, self._gradflat[a:b].view(t.shape)))
+
+    def _pack(self):
+        return self._flat
+
+    def _scatter_grad(self, flat_grad):
+        self._gradflat.copy_(flat_grad)
+        for t, g in self._grad_views:
+            t.grad = g
 
     # ------------------------------------------------------------------ training
     def meta_fit(self, valid_tuples=None, verbose=True, log_period=500, n_iter=None):
@@ -255,7 +271,7 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
             self.shared_parameters.append({'params': [self.constant_mean], 'lr': self.lr_params})
         self.arch = eng.GPArch(self.input_dim, mean_kind=mean_module, covar_kind=covar_module,
                                mean_layers=tuple(mean_nn_layers), kernel_layers=tuple(kernel_nn_layers),
-                               feature_dim=feature_dim, outputscale=True, noise_floor=1e-3)
+                               feature_dim=feature_dim, outputscale=True, noise_floor=self.NOISE_FLOOR)
         self._last_info = None
 
     def _setup_optimizer(self, optimizer, lr, lr_decay):

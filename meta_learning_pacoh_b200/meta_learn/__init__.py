@@ -3,5 +3,6 @@
 from .GPR_meta_mll import GPRegressionMetaLearned
 from .GPR_meta_vi import GPRegressionMetaLearnedVI
 from .GPR_meta_svgd import GPRegressionMetaLearnedSVGD
+from .GPR_mll import GPRegressionLearned
 
-__all__ = ["GPRegressionMetaLearned", "GPRegressionMetaLearnedVI", "GPRegressionMetaLearnedSVGD"]
+__all__ = ["GPRegressionMetaLearned", "GPRegressionMetaLearnedVI", "GPRegressionMetaLearnedSVGD", "GPRegressionLearned"]

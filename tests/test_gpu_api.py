@@ -291,3 +291,32 @@ def test_graph_replayed_steps_equal_eager_steps(ml, monkeypatch, kind):
     torch.manual_seed(7)
     b.meta_fit(verbose=False, log_period=10, n_iter=12)
     assert torch.equal(params(a), params(b))
+
+
+# ---------------------------------------------------------------------------------------------- single-task sibling
+def test_single_task_learner_like_reference_tests(ml):
+    """GPRegressionLearned (meta_learn/GPR_mll.py:11-216): the behavioural checks of the reference's tests/test_GPR.py::TestGPR_mll
+    -- seed determinism (:35-48), learning improves the fit (:76-100) -- plus the first loss against the oracle's MLL."""
+    rs = np.random.RandomState(22)
+    x = rs.uniform(-3, 3, size=(30, 1)); t = np.sin(2 * x) + 0.1 * rs.normal(size=(30, 1)) + 0.5 * x
+    xv = rs.uniform(-3, 3, size=(40, 1)); tv = np.sin(2 * xv) + 0.1 * rs.normal(size=(40, 1)) + 0.5 * xv
+    a = ml.GPRegressionLearned(x, t, num_iter_fit=60, random_seed=22)
+    b = ml.GPRegressionLearned(x, t, num_iter_fit=60, random_seed=22)
+    ll0, rmse0, _ = a.eval(xv, tv)
+    la = a.fit(valid_x=xv, valid_t=tv, verbose=False, log_period=30)
+    lb = b.fit(valid_x=xv, valid_t=tv, verbose=False, log_period=30)
+    assert la == lb and np.array_equal(a.predict(xv)[0], b.predict(xv)[0])            # seed determinism
+    ll1, rmse1, _ = a.eval(xv, tv)
+    assert ll1 > ll0 and a.fitted
+    mean, std = a.predict(xv.flatten())
+    assert mean.shape == (40,) and (std > 0).all()
+    ucb, lcb = a.confidence_intervals(xv.flatten())
+    assert (ucb.numpy() > lcb.numpy()).all()
+    # first-iteration loss = - mll of the (normalised) training set under the initial parameters, noise floor 1e-4
+    c = ml.GPRegressionLearned(x, t, random_seed=5)
+    lay = orc.Layout(1, outputscale=True, noise_floor=1e-4)
+    theta = c._pack().cpu().double()
+    xn, tn = c._normalize_data(x, t)
+    want = -orc.task_mll(theta, lay, torch.from_numpy(xn), torch.from_numpy(tn.flatten()))
+    got = c._loss_and_grad(np.zeros(1, dtype=np.int32))
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))

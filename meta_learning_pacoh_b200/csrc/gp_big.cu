@@ -42,15 +42,15 @@ using namespace tc;
 
 constexpr int NB = 128;                 // tile edge
 constexpr int KC = 32;                  // K chunk = one TMA box / one pipeline stage
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
 constexpr int kConv = 256;              // converter / flush / epilogue threads (warps 0-7)
 constexpr int kBigThreads = 320;        // + warp 8 (TMA producer) + warp 9 (MMA issuer, tensor-memory owner)
 constexpr float kFarB = 1.0e18f;
 constexpr float kCB = 0.84932180028801904272f;   // sqrt(0.5 * log2(e))
 
 constexpr uint32_t kStageBytes = 3 * 16384;                // raw A | raw B | lo B
-constexpr uint32_t kOffTile = NSTAGE * kStageBytes;        // 147456
-constexpr uint32_t kTileBytes = NB * LDT * 4;              // 67584
+constexpr uint32_t kOffTile = NSTAGE * kStageBytes;        // 196608: scratch of the epilogues (column sums, row exchange)
+constexpr uint32_t kTileBytes = 2048 * 4 + 1024 * 4 + 256;
 constexpr uint32_t kOffUcol = kOffTile + kTileBytes;       // float4[128]
 constexpr uint32_t kOffAcol = kOffUcol + 2048;             // float[128]
 constexpr uint32_t kOffMisc = kOffAcol + 512;              // float[128] scratch
@@ -143,16 +143,15 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  // barriers: full_raw[3] | conv_done[3] | mma_done[3] | d_full[2] | d_free[2] | epi_done
+  // barriers: full_raw[NSTAGE] | conv_done[NSTAGE] | mma_done[NSTAGE] | d_full[2] | d_free[2] | (spare)
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
-  auto CONV = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto MMAD = [&](int s) { return bar0 + 8u * (6 + s); };
-  auto DFULL = [&](int d) { return bar0 + 8u * (9 + d); };
-  auto DFREE = [&](int d) { return bar0 + 8u * (11 + d); };
-  const uint32_t EPI = bar0 + 8u * 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * 14);
-  float* pd_flag = reinterpret_cast<float*>(smem + kOffBar + 8 * 15);
+  auto CONV = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto MMAD = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+  auto DFULL = [&](int d) { return bar0 + 8u * (3 * NSTAGE + d); };
+  auto DFREE = [&](int d) { return bar0 + 8u * (3 * NSTAGE + 2 + d); };
+  const uint32_t EPI = bar0 + 8u * (3 * NSTAGE + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (3 * NSTAGE + 5));
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // SWIZZLE_128B tiles need a 1024-byte aligned base
 
   if (tid == 0) {
@@ -202,7 +201,6 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const Item it = decode(item);
         if (it.skip) continue;
-        if (MODE == M_DIAG && nitem > 0) mbar_wait(EPI, (nitem - 1) & 1);   // the epilogue borrows the stage memory
         ++nitem;
         const int sbz = (it.m * a.nb_max) * 2;
         const int ns = nsub_of(it);
@@ -440,64 +438,28 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
           for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
           flush(bb);
           ++bb;
-          // result tile -> shared memory -> global, coalesced
-          conv_sync();
+          // result tile -> global straight from the registers: this thread owns 64 consecutive floats of row r (a warp's store
+          // covers 32 rows x 16 bytes; the L2 merges the sector halves).  No staging tile: its 66 KB buy a fourth pipeline stage.
+          {
+            float* dst = a.Lbuf + ((size_t)it.m * a.npad + (size_t)it.ti * NB + r) * a.npad + (size_t)it.tj * NB + 64 * h;
 #pragma unroll
-          for (int i4 = 0; i4 < 16; ++i4)
-            sts4(T + r * LDT + 64 * h + 4 * i4, make_float4(acc[4 * i4], acc[4 * i4 + 1], acc[4 * i4 + 2], acc[4 * i4 + 3]));
-          conv_sync();
-          float* dst = a.Lbuf + ((size_t)it.m * a.npad + (size_t)it.ti * NB) * a.npad + (size_t)it.tj * NB;
-#pragma unroll 4
-          for (int rr = warp; rr < NB; rr += 8)
-            *reinterpret_cast<float4*>(dst + (size_t)rr * a.npad + 4 * lane) = lds4(T + rr * LDT + 4 * lane);
+            for (int i4 = 0; i4 < 16; ++i4)
+              *reinterpret_cast<float4*>(dst + 4 * i4) = make_float4(acc[4 * i4], acc[4 * i4 + 1], acc[4 * i4 + 2], acc[4 * i4 + 3]);
+          }
         }
 
         if (MODE == M_DIAG) {
-          // ------------------------------------------------------------ diagonal tile: potrf, trtri, v_k, log det
-          float* X = reinterpret_cast<float*>(smem);          // stage memory (the producer waits for EPI)
+          // ------------------------------------------------------------ diagonal tile: write C_kk = Khat_kk - sum_j L_kj L_kj^T
+          //      and rhs_k = r_k - sum_j L_kj v_j; big_potrf_kernel factorises it (3 CTAs per SM: its serial sections
+          //      would otherwise stall this kernel's tensor pipeline)
           conv_sync();
+          if (h == 1) misc[r] = tdot;
+          conv_sync();
+          if (h == 0) a.vbuf[vecoff + row] = a.rbuf[vecoff + row] - (tdot + misc[r]);
+          float* dst = a.Lbuf + ((size_t)it.m * a.npad + (size_t)step * NB + r) * a.npad + (size_t)step * NB + 64 * h;
 #pragma unroll
           for (int i4 = 0; i4 < 16; ++i4)
-            sts4(T + r * LDT + 64 * h + 4 * i4, make_float4(acc[4 * i4], acc[4 * i4 + 1], acc[4 * i4 + 2], acc[4 * i4 + 3]));
-          if (h == 1) misc[r] = tdot;
-          const bool ok = potrf_trtri_128(T, X, tid, pd_flag);
-          if (!ok && tid == 0) atomicExch(&a.mat[it.m].fail, 1);
-          // rhs_r = r_k - sum_j L_kj v_j ; v_k[c] = sum_{r <= c} U[r][c] rhs_r ; log2 det
-          if (h == 0) {
-            const float rhs = a.rbuf[vecoff + row] - (tdot + misc[r]);
-            misc[r] = rhs;
-          }
-          conv_sync();
-          if (h == 0) {
-            float vk = 0.0f;
-            for (int rr = 0; rr <= r; ++rr) vk = fmaf(X[rr * LDT + r], misc[rr], vk);
-            a.vbuf[vecoff + row] = vk;
-            float lg = log2f(T[r * LDT + r]);
-            lg = warp_sum(lg);
-            if (lane == 0) acolv[warp] = lg;
-          }
-          conv_sync();
-          if (tid == 0) a.ldet[(size_t)it.m * a.nb_max + step] = (acolv[0] + acolv[1]) + (acolv[2] + acolv[3]);
-          // L_kk (zeros above the diagonal) -> Lbuf ; U_kk -> SB[.][k][1] ; L_kk^-1 = U_kk^T -> SB[.][k][0]
-          float* dstL = a.Lbuf + ((size_t)it.m * a.npad + (size_t)step * NB) * a.npad + (size_t)step * NB;
-          float* dstI = a.SB + ((size_t)it.m * a.nb_max + step) * 2 * NB * NB;
-          float* dstU = dstI + NB * NB;
-          for (int rr = warp; rr < NB; rr += 8) {
-            float4 l = lds4(T + rr * LDT + 4 * lane);
-            const int cb = 4 * lane;
-            if (cb + 0 > rr) l.x = 0.0f;
-            if (cb + 1 > rr) l.y = 0.0f;
-            if (cb + 2 > rr) l.z = 0.0f;
-            if (cb + 3 > rr) l.w = 0.0f;
-            *reinterpret_cast<float4*>(dstL + (size_t)rr * a.npad + cb) = l;
-            *reinterpret_cast<float4*>(dstU + rr * NB + cb) = lds4(X + rr * LDT + cb);
-            // row rr of L^-1 = column rr of U
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dstI[rr * NB + lane + 32 * e] = X[(lane + 32 * e) * LDT + rr];
-          }
-          conv_sync();
-          fence_async_smem();          // generic-proxy writes to the stage memory before the next TMA overwrites it
-          mbar_arrive(EPI);
+            *reinterpret_cast<float4*>(dst + 4 * i4) = make_float4(acc[4 * i4], acc[4 * i4 + 1], acc[4 * i4 + 2], acc[4 * i4 + 3]);
         }
 
         if (MODE == M_GRAD) {
@@ -576,10 +538,10 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
       if (MODE == M_GRAD) {
         // the row sums of this block row (two column halves per row) and the diagonal of Khat^-1
         conv_sync();
-        if (h == 1) { float* o = T + r * 8; o[1] = S1[0]; o[2] = S1[1]; o[3] = S1[2]; o[4] = S1[3]; o[5] = trc; }
+        if (h == 1) { float* o = T + 2048 + r * 8; o[1] = S1[0]; o[2] = S1[1]; o[3] = S1[2]; o[4] = S1[3]; o[5] = trc; }
         conv_sync();
         if (h == 0) {
-          const float* o = T + r * 8;
+          const float* o = T + 2048 + r * 8;
           float* dst = a.rowpart + (vecoff + row) * 8;
           *reinterpret_cast<float4*>(dst) = make_float4(S1[0] + o[1], S1[1] + o[2], S1[2] + o[3], S1[3] + o[4]);
           dst[4] = trc + o[5];
@@ -590,6 +552,65 @@ big_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUt
   fence_before_sync();
   __syncthreads();
   if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Diagonal tile k of every matrix: C_kk (written by big_kernel<M_DIAG>) -> L_kk, L_kk^-1, U_kk = L_kk^-T, v_k = L_kk^-1 rhs_k,
+// sum log2 L_ii.  One CTA (256 threads, one 67.5 KB tile: L below the diagonal, U above it) per matrix, three CTAs per SM:
+// the factorisation is a chain of short serial sections (32-column panels) that only other resident CTAs can hide.
+__global__ void __launch_bounds__(256, 3) big_potrf_kernel(BigArgs a, int step) {
+  extern __shared__ __align__(16) float smp[];
+  float* T = smp;
+  float* rhs = smp + NB * LDT;
+  float* red = rhs + NB;
+  float* flag = red + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nmat = a.list != nullptr ? __ldg(a.count) : a.B;
+  for (int ml = blockIdx.x; ml < nmat; ml += gridDim.x) {
+    const int m = a.list != nullptr ? __ldg(a.list + ml) : ml;
+    if (step >= a.mat[m].nb) continue;
+    const size_t vecoff = (size_t)m * a.npad;
+    float* tileL = a.Lbuf + ((size_t)m * a.npad + (size_t)step * NB) * a.npad + (size_t)step * NB;
+    conv_sync();
+    for (int rr = warp; rr < NB; rr += 8) sts4(T + rr * LDT + 4 * lane, *reinterpret_cast<const float4*>(tileL + (size_t)rr * a.npad + 4 * lane));
+    if (tid < NB) rhs[tid] = a.vbuf[vecoff + step * NB + tid];
+    const bool ok = potrf_trtri_128_inplace(T, tid, flag);
+    if (!ok && tid == 0) atomicExch(&a.mat[m].fail, 1);
+    if (tid < NB) {                     // v_k[c] = sum_{r <= c} U[r][c] rhs_r ; log2 det
+      const int c = tid;
+      const float ucc = 1.0f / T[c * LDT + c];
+      float vk = ucc * rhs[c];
+      for (int rr = 0; rr < c; ++rr) vk = fmaf(T[rr * LDT + c], rhs[rr], vk);
+      a.vbuf[vecoff + step * NB + c] = vk;
+      float lg = log2f(T[c * LDT + c]);
+      lg = warp_sum(lg);
+      if (lane == 0) red[warp] = lg;
+    }
+    conv_sync();
+    if (tid == 0) a.ldet[(size_t)m * a.nb_max + step] = (red[0] + red[1]) + (red[2] + red[3]);
+    // L_kk (zeros above the diagonal) -> Lbuf ; U_kk -> SB[.][k][1] ; L_kk^-1 = U_kk^T -> SB[.][k][0]
+    float* dstI = a.SB + ((size_t)m * a.nb_max + step) * 2 * NB * NB;
+    float* dstU = dstI + NB * NB;
+    for (int rr = warp; rr < NB; rr += 8) {
+      const float4 t4 = lds4(T + rr * LDT + 4 * lane);
+      const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+      const float inv_d = 1.0f / T[rr * LDT + rr];
+      float lo[4], up[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cc = 4 * lane + e;
+        lo[e] = cc <= rr ? tv[e] : 0.0f;
+        up[e] = cc > rr ? tv[e] : (cc == rr ? inv_d : 0.0f);
+      }
+      *reinterpret_cast<float4*>(tileL + (size_t)rr * a.npad + 4 * lane) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<float4*>(dstU + rr * NB + 4 * lane) = make_float4(up[0], up[1], up[2], up[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {      // row rr of L^-1 = column rr of U
+        const int cr = lane + 32 * e;    // U[cr][rr]
+        dstI[rr * NB + cr] = cr < rr ? T[cr * LDT + rr] : (cr == rr ? inv_d : 0.0f);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -998,6 +1019,14 @@ int launch_gp_mll_big(const GpArgs& g, void* ws, size_t ws_bytes, cudaStream_t s
       }
       for (int k = 0; k < L.nb; ++k) {
         if ((rc = launch_big<M_DIAG>(mL, mS, a, k, 1, st)) != PACOH_OK) return rc;
+        {
+          static bool once = false;
+          const int psmem = (NB * LDT + NB + 16) * 4;
+          if (!once) { PACOH_CUDA_CHECK(cudaFuncSetAttribute(big_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)); once = true; }
+          const int pgrid = a.list != nullptr ? std::min(a.B, 64) : std::min(a.B, 3 * grid_for(1 << 30));
+          big_potrf_kernel<<<pgrid, 256, psmem, st>>>(a, k);
+          PACOH_CUDA_CHECK(cudaGetLastError());
+        }
         if ((rc = launch_big<M_PANEL>(mL, mS, a, k, L.nb - k - 1, st)) != PACOH_OK) return rc;
       }
     }

@@ -246,6 +246,11 @@ int pacoh_step_prepare(void* state, int32_t K, int32_t T, const int32_t* idx_str
                        void* stream);
 int pacoh_adam_step_dev(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg, float* exp_avg_sq,
                         float beta1, float beta2, float eps, const void* state, void* stream);
+/* torch.optim.AdamW on a flat parameter buffer (PACOH-MAP: GPR_meta_mll.py:253-257, decay on every group): decoupled weight
+ * decay p *= 1 - lr * weight_decay, then the Adam update; `mask` (count bytes, may be NULL) freezes the entries that are 0. */
+int pacoh_adamw_step_dev(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg, float* exp_avg_sq,
+                         float beta1, float beta2, float eps, float weight_decay, const uint8_t* mask, const void* state,
+                         void* stream);
 
 /*
  * Host-only helper: the persistent schedule of the tensor-core MLP backward kernel (one CTA per SM per wave, the

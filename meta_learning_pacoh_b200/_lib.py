@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pacoh_workspace_bytes", "pacoh_meta_mll_fwd_bwd", "pacoh_meta_mll_fwd_bwd_ragged", "pacoh_mlp_bwd_schedule", "pacoh_logprob_finalize", "pacoh_peer_allreduce_finalize", "pacoh_svgd_workspace_bytes",
     "pacoh_svgd_phi", "pacoh_svgd_kernel_matrix", "pacoh_svgd_phi_apply", "pacoh_vi_sample", "pacoh_vi_grad", "pacoh_ffma_peak_launch", "pacoh_adam_step",
     "pacoh_stage_timing_enable", "pacoh_stage_timing_read", "pacoh_gp_forward", "pacoh_gp_forward_workspace_bytes",
-    "pacoh_debug_big_layout", "pacoh_peer_allreduce_finalize_dev", "pacoh_step_prepare", "pacoh_adam_step_dev",
+    "pacoh_debug_big_layout", "pacoh_peer_allreduce_finalize_dev", "pacoh_step_prepare", "pacoh_adam_step_dev", "pacoh_adamw_step_dev",
     "pacoh_gp_posterior_workspace_bytes", "pacoh_gp_posterior", "pacoh_pred_metrics",
 ]
 
@@ -86,6 +86,8 @@ def _load():
     lib.pacoh_gp_posterior.argtypes = [archp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.pacoh_pred_metrics.restype = ctypes.c_int
     lib.pacoh_pred_metrics.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp]
+    lib.pacoh_adamw_step_dev.restype = ctypes.c_int
+    lib.pacoh_adamw_step_dev.argtypes = [i64, vp, vp, f32, vp, vp, f32, f32, f32, f32, vp, vp, vp]
     lib.pacoh_svgd_workspace_bytes.restype = i64
     lib.pacoh_svgd_workspace_bytes.argtypes = [i32, i64]
     lib.pacoh_svgd_phi.restype = ctypes.c_int

@@ -218,6 +218,23 @@ __global__ void adam_dev_kernel(int64_t count, float* __restrict__ p, const floa
   p[i] -= step_size * (mi / denom);
 }
 
+// torch.optim.AdamW (decoupled weight decay: p *= 1 - lr wd before the Adam update) with the step-dependent scalars on the
+// device; `mask` (optional) freezes entries (PACOH-MAP learning modes that train only the mean or only the kernel).
+__global__ void adamw_dev_kernel(int64_t count, float* __restrict__ p, const float* __restrict__ g, float gsign,
+                                 float* __restrict__ m, float* __restrict__ v, float beta1, float beta2, float eps, float wd,
+                                 const unsigned char* __restrict__ mask, const float* __restrict__ state) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count || (mask != nullptr && mask[i] == 0)) return;
+  const float lr = state[2], step_size = state[3], inv_sqrt_bc2 = state[4];
+  const float gr = gsign * g[i];
+  const float pi = p[i] * (1.0f - lr * wd);
+  const float mi = m[i] + (gr - m[i]) * (1.0f - beta1);
+  const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gr * gr);
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  p[i] = pi - step_size * (mi / denom);
+}
+
 // One block: advances the step counter, derives the learning rate (StepLR) and Adam's bias corrections for the new step,
 // and copies slot (old step mod K) of the pre-uploaded index / float streams into the fixed buffers the step's kernels read.
 __global__ void step_prepare_kernel(int* __restrict__ state, int K, int T, const int* __restrict__ idx_stream, int* __restrict__ idx_out,
@@ -362,6 +379,20 @@ extern "C" int pacoh_adam_step_dev(int64_t count, float* param, const float* gra
   }
   adam_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(count, param, grad, grad_sign, exp_avg, exp_avg_sq,
                                                                                     beta1, beta2, eps, (const float*)state);
+  PACOH_CUDA_CHECK(cudaGetLastError());
+  return PACOH_OK;
+}
+
+extern "C" int pacoh_adamw_step_dev(int64_t count, float* param, const float* grad, float grad_sign, float* exp_avg,
+                                    float* exp_avg_sq, float beta1, float beta2, float eps, float weight_decay,
+                                    const uint8_t* mask, const void* state, void* stream) {
+  if (count < 1 || !param || !grad || !exp_avg || !exp_avg_sq || !state) {
+    set_error("pacoh_adamw_step_dev: invalid argument");
+    return PACOH_ERR_INVALID;
+  }
+  adamw_dev_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(count, param, grad, grad_sign, exp_avg, exp_avg_sq,
+                                                                                     beta1, beta2, eps, weight_decay, mask,
+                                                                                     (const float*)state);
   PACOH_CUDA_CHECK(cudaGetLastError());
   return PACOH_OK;
 }

@@ -5,6 +5,7 @@ layout, evaluates loss = -sum_{t in batch} mll_t and its gradient with ONE pacoh
 ScaleKernel outputscale, noise floor 1e-3) instead of the per-task loop (GPR_meta_mll.py:109-113), and scatters the
 gradient back into ``.grad`` for torch's AdamW / SGD.
 """
+import os
 import time
 from collections import OrderedDict
 
@@ -36,6 +37,24 @@ class NeuralNetwork(torch.nn.Sequential):
         for lin in self.linears()[:-1]:
             x = torch.tanh(lin(x))
         return self.out(x)
+
+
+class _SyncedAdamW(torch.optim.AdamW):
+    """torch.optim.AdamW whose moment buffers are views of the learner's flat (D,) buffers and whose step count mirrors the
+    learner's device-side step state: the fused device step (pacoh_adamw_step_dev) and torch's own ``step()`` advance the SAME
+    optimizer state, and ``state_dict()`` keeps torch's format (GPR_meta_mll.py:192-205 checkpoints)."""
+
+    owner = None
+
+    def step(self, closure=None):
+        o = self.owner
+        if o is not None:
+            o._sync_step_tensors()
+        out = super().step(closure)
+        if o is not None:
+            o._state.steps += 1
+            o._state.buf[0:1].fill_(o._state.steps)
+        return out
 
 
 class GPRegressionMetaLearned(RegressionModelMetaLearned):
@@ -110,6 +129,33 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
             if trainable:
                 self._grad_views.append((t, self._gradflat[a:b].view(t.shape)))
 
+    def _link_optimizer_state(self):
+        """Moment buffers of every trainable parameter = views of the flat (D,) buffers the fused AdamW kernel updates."""
+        D = self.arch.D
+        if not hasattr(self, "_mflat"):
+            self._mflat = torch.zeros(D, dtype=torch.float32, device=self.device)
+            self._vflat = torch.zeros(D, dtype=torch.float32, device=self.device)
+            self._mask = torch.zeros(D, dtype=torch.uint8, device=self.device)
+        trainable = {id(t) for t, _ in self._grad_views}
+        for (name, t), (a, b) in zip(self._named_flat(), self.arch.entries().values()):
+            if id(t) not in trainable:
+                continue
+            self._mask[a:b] = 1
+            st = self.optimizer.state[t]
+            if "exp_avg" in st:                       # loaded from a checkpoint: adopt the values, then alias
+                self._mflat[a:b].copy_(st["exp_avg"].reshape(-1))
+                self._vflat[a:b].copy_(st["exp_avg_sq"].reshape(-1))
+                self._state.steps = int(float(st["step"]))
+            st["step"] = torch.tensor(float(self._state.steps))
+            st["exp_avg"] = self._mflat[a:b].view(t.shape)
+            st["exp_avg_sq"] = self._vflat[a:b].view(t.shape)
+        self._state.buf[0:1].fill_(self._state.steps)
+
+    def _sync_step_tensors(self):
+        for st in self.optimizer.state.values():
+            if "step" in st:
+                st["step"].fill_(float(self._state.steps))
+
     def _pack(self):
         return self._flat
 
@@ -127,17 +173,19 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         # shared parameter, GPR_meta_mll.py:56): 'vanilla' mode still trains the noise
         if len(self.shared_parameters) > 0:
             t = time.time()
-            cum_loss = torch.zeros((), device=self.device)
             if n_iter is None:
                 n_iter = self.num_iter_fit
-            for itr in range(1, n_iter + 1):
-                loss = self.map_step(self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size))
-                cum_loss = cum_loss + loss
+            itr = 0
+            self._cum_loss.zero_()
+            while itr < n_iter:
+                nxt = 1 if itr == 0 else min(n_iter, (itr // log_period + 1) * log_period)
+                loss = self.run_steps(nxt - itr)
+                itr = nxt
                 if itr == 1 or itr % log_period == 0:
                     self._failures.check()
                     duration = time.time() - t
-                    avg_loss = cum_loss / (log_period if itr > 1 else 1.0)
-                    cum_loss = torch.zeros((), device=self.device)
+                    avg_loss = self._cum_loss / (log_period if itr > 1 else 1.0)     # GPR_meta_mll.py:119-126
+                    self._cum_loss.zero_()                                           # in place: a captured graph accumulates into it
                     t = time.time()
                     message = 'Iter %d/%d - Loss: %.6f - Time %.2f sec' % (itr, self.num_iter_fit, avg_loss.item(), duration)
                     if valid_tuples is not None:
@@ -151,19 +199,74 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         self.fitted = True
         return loss.item()
 
+    GRAPH_STEPS = 10
+
+    def _device_step(self, K, idx_stream):
+        """One iteration with every step-dependent scalar on the device (capture-safe): batch hand-over + step state,
+        batched MLL forward + backward, [cross-rank sum], fused AdamW on the flat parameter buffer (the modules are views of it)."""
+        st, D = self._state, self.arch.D
+        st.prepare(K, self._idx_cur.numel(), idx_stream, self._idx_cur)
+        _, packed, info = self.engine.mll_fwd_bwd(self._flat, self._idx_cur, want_mll=False, want_info=True)
+        if getattr(self, "_world", 1) > 1:
+            torch.distributed.all_reduce(packed, group=self._group)
+        g = self.optimizer.param_groups[0]
+        eng.check(eng.lib.pacoh_adamw_step_dev(D, eng._ptr(self._flat), eng._ptr(packed), -1.0, eng._ptr(self._mflat), eng._ptr(self._vflat),
+                                               float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(self.weight_decay),
+                                               eng._ptr(self._mask), eng._ptr(st.buf), eng._stream()))      # grad = -d sum mll
+        self._failures.update(info)
+        loss = -packed[D]
+        self._cum_loss += loss
+        return loss, info
+
     def map_step(self, task_idx):
         """One iteration of the meta_fit loop body on the given batch (GPR_meta_mll.py:107-117): zero_grad, loss = - sum of the
         batch's MLLs, backward, optimizer step, lr schedule.  Returns the loss (device scalar)."""
-        self.optimizer.zero_grad()
-        loss = self._loss_and_grad(task_idx)
-        self.optimizer.step()
+        if self._state is None:                    # optimizer='SGD': torch's optimizer on the scattered gradient
+            self.optimizer.zero_grad()
+            loss = self._loss_and_grad(task_idx)
+            self.optimizer.step()
+            self.lr_scheduler.step()
+            self._cum_loss += loss
+            return loss
+        idx = np.asarray(task_idx, dtype=np.int32)
+        world, rank = getattr(self, "_world", 1), getattr(self, "_rank", 0)
+        assert len(idx) >= world, "task batch smaller than the number of ranks"
+        lo, hi = eng.shard_bounds(len(idx), rank, world)
+        if self._idx_cur is None or self._idx_cur.numel() != hi - lo:
+            self._idx_cur = torch.empty(hi - lo, dtype=torch.int32, device=self.device)
+            self._graph = None
+        loss, self._last_info = self._device_step(1, self._idx_ring.upload(idx[lo:hi]))
         self.lr_scheduler.step()
         return loss
 
     def run_steps(self, n):
+        """``n`` iterations of the meta_fit loop (GPR_meta_mll.py:104-117); with AdamW and equally sized tasks GRAPH_STEPS of them
+        replay from one CUDA graph (PACOH_GRAPH=0: always eager), bitwise identical to the eager sequence."""
         loss = None
-        for _ in range(n):
-            loss = self.map_step(self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size))
+        K = self.GRAPH_STEPS
+        use_graph = self._state is not None and not self._ragged and os.environ.get("PACOH_GRAPH", "1") != "0"
+        world, rank = getattr(self, "_world", 1), getattr(self, "_rank", 0)
+        while n > 0:
+            lo, hi = eng.shard_bounds(self.task_batch_size, rank, world)
+            if use_graph and n >= K and self._state.steps > 0 and self._idx_cur is not None and self._idx_cur.numel() == hi - lo:
+                if self._graph is None:
+                    self._idx_stream = torch.zeros(K, hi - lo, dtype=torch.int32, device=self.device)
+                    s0 = self._state.steps
+                    self._graph = eng.StepGraph(lambda: self._device_step(K, self._idx_stream), K, self.device)
+                    self._state.steps = s0          # the capture only recorded: nothing ran
+                s0 = self._state.steps
+                rows = np.empty((K, hi - lo), dtype=np.int32)
+                for j in range(K):
+                    rows[(s0 + j) % K] = self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size)[lo:hi]
+                self._idx_ring.upload(rows, out=self._idx_stream)
+                loss, self._last_info = self._graph.replay()
+                self._state.steps += K
+                for _ in range(K):
+                    self.lr_scheduler.step()
+                n -= K
+            else:
+                loss = self.map_step(self.rds_numpy.choice(len(self.task_dicts), size=self.task_batch_size))
+                n -= 1
         return loss
 
     def shard_tasks(self, group=None):
@@ -224,6 +327,8 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         # deep copy: torch >= 2 no longer copies optimizer state tensors in load_state_dict, so a snapshot that aliases
         # the live exp_avg buffers would be shared between two learners
         import copy
+        if self._state is not None:
+            self._sync_step_tensors()
         return {'optimizer': copy.deepcopy(self.optimizer.state_dict()), 'model': self._model_state()}
 
     def load_state_dict(self, state_dict):
@@ -238,6 +343,9 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
             if net is not None:
                 net.load_state_dict({k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + '.')})
         self.optimizer.load_state_dict(state_dict['optimizer'])
+        if self._state is not None:
+            self._link_optimizer_state()
+            self._graph = None
 
     # ------------------------------------------------------------------ setup
     def _setup_gp_prior(self, mean_module, covar_module, learning_mode, feature_dim, mean_nn_layers, kernel_nn_layers):
@@ -277,8 +385,13 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
     def _setup_optimizer(self, optimizer, lr, lr_decay):
         # AdamW's constructor-level weight_decay also applies to the groups that did not set one (likelihood, covar,
         # mean hypers) -- a reference quirk pinned by the demo.ipynb trajectory (GPR_meta_mll.py:56, 248-255)
+        self._state, self._graph, self._idx_cur = None, None, None
+        self._cum_loss = torch.zeros((), device=self.device)
         if optimizer == 'Adam':
-            self.optimizer = torch.optim.AdamW(self.shared_parameters, lr=lr, weight_decay=self.weight_decay)
+            self.optimizer = _SyncedAdamW(self.shared_parameters, lr=lr, weight_decay=self.weight_decay)
+            self.optimizer.owner = self
+            self._state = eng.StepState(self.device, lr, lr_decay)       # lr, StepLR(1000, lr_decay), AdamW step count on the device
+            self._link_optimizer_state()
         elif optimizer == 'SGD':
             self.optimizer = torch.optim.SGD(self.shared_parameters, lr=lr)
         else:

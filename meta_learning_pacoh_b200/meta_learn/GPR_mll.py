@@ -38,6 +38,8 @@ class GPRegressionLearned(GPRegressionMetaLearned):
         self.parameters = self.shared_parameters
 
     def _setup_optimizer(self, optimizer, lr, lr_decay):
+        self._state, self._graph, self._idx_cur = None, None, None       # torch's optimizer owns the state here (plateau scheduler)
+        self._cum_loss = torch.zeros((), device=self.device)
         if optimizer == 'Adam':
             self.optimizer = torch.optim.AdamW(self.shared_parameters)        # torch defaults for groups that set nothing (GPR_mll.py:101)
         elif optimizer == 'SGD':

@@ -259,7 +259,7 @@ def test_map_module_variants_train(ml, kw):
 
 
 # ---------------------------------------------------------------------------------------------- CUDA-graph replayed steps
-@pytest.mark.parametrize("kind", ["svgd", "vi"])
+@pytest.mark.parametrize("kind", ["svgd", "vi", "map"])
 def test_graph_replayed_steps_equal_eager_steps(ml, monkeypatch, kind):
     """run_steps replays GRAPH_STEPS steps per CUDA graph (device-side step state, pre-uploaded index / normal-draw
     streams: SURVEY 8(f).2); the result must be BITWISE what the eager step sequence gives, lr decay included."""
@@ -268,9 +268,14 @@ def test_graph_replayed_steps_equal_eager_steps(ml, monkeypatch, kind):
     def make():
         if kind == "svgd":
             return ml.GPRegressionMetaLearnedSVGD(train, num_particles=10, lr=2e-3, lr_decay=0.5, random_seed=30)
+        if kind == "map":
+            return ml.GPRegressionMetaLearned(train, lr_params=2e-3, weight_decay=0.1, lr_decay=0.5, learning_mode="learn_kernel",
+                                              mean_module="constant", random_seed=30)
         return ml.GPRegressionMetaLearnedVI(train, svi_batch_size=8, lr=2e-3, lr_decay=0.5, random_seed=30)
 
     def params(m):
+        if kind == "map":
+            return m._flat.clone()
         return m.particles if kind == "svgd" else torch.cat([m.posterior.loc.detach(), m.posterior.scale.detach()])
 
     monkeypatch.setenv("PACOH_GRAPH", "0")
@@ -284,8 +289,11 @@ def test_graph_replayed_steps_equal_eager_steps(ml, monkeypatch, kind):
     assert b._graph is not None
     assert torch.equal(params(a), params(b))
     assert a._state.steps == b._state.steps == 37
+    if kind == "map":
+        b._sync_step_tensors()
+        assert float((b._flat - a._flat).abs().max()) == 0.0 and float(b.constant_mean.detach()) == 0.0     # frozen by the mask
     st = b.optimizer.state[next(iter(b.optimizer.state))]
-    assert st["step"] == 37
+    assert float(st["step"]) == 37
     torch.manual_seed(7)                                       # VI draws its normals from the (shared) global CPU generator
     a.meta_fit(verbose=False, log_period=10, n_iter=12)        # meta_fit goes through the same path and stays in sync
     torch.manual_seed(7)
@@ -320,3 +328,26 @@ def test_single_task_learner_like_reference_tests(ml):
     want = -orc.task_mll(theta, lay, torch.from_numpy(xn), torch.from_numpy(tn.flatten()))
     got = c._loss_and_grad(np.zeros(1, dtype=np.int32))
     assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+
+
+def test_map_fused_adamw_equals_torch_adamw(ml, monkeypatch):
+    """The fused device-state AdamW (pacoh_adamw_step_dev) against torch.optim.AdamW on the same gradients: 30 steps with
+    weight decay and StepLR(1000), stepped through the learner's torch path (zero_grad / _loss_and_grad / optimizer.step)."""
+    monkeypatch.setenv("PACOH_GRAPH", "0")
+    train = orc.sinusoid_tasks(20, 5, seed=26)
+    a = ml.GPRegressionMetaLearned(train, weight_decay=0.2, lr_decay=0.9, random_seed=30)
+    b = ml.GPRegressionMetaLearned(train, weight_decay=0.2, lr_decay=0.9, random_seed=30)
+    for _ in range(30):
+        idx = a.rds_numpy.choice(20, size=5)
+        assert np.array_equal(idx, b.rds_numpy.choice(20, size=5))
+        a.map_step(idx)                                   # fused path
+        b.optimizer.zero_grad(); b._loss_and_grad(idx); b.optimizer.step(); b.lr_scheduler.step()     # torch path
+    assert a._state.steps == b._state.steps == 30
+    # the kernel net's output bias has a numerically ZERO gradient (shift invariance): Adam normalises that rounding noise to
+    # +-lr steps, so two correct implementations random-walk it differently (the reference's own path does too): leave it out
+    lo, hi = a.arch.entries()["kernel_nn.out.bias"]
+    keep = torch.ones(a.arch.D, dtype=torch.bool, device=a._flat.device)
+    keep[lo:hi] = False
+    assert float((a._flat - b._flat)[0, keep].abs().max()) <= 1e-5 * float(b._flat.abs().max())
+    assert float((a._mflat - b._mflat)[keep].abs().max()) <= 1e-5 * float(b._mflat.abs().max())
+    assert float((a._vflat - b._vflat)[keep].abs().max()) <= 1e-5 * float(b._vflat.abs().max())

@@ -244,8 +244,10 @@ class GPRegressionMetaLearned(RegressionModelMetaLearned):
         replay from one CUDA graph (PACOH_GRAPH=0: always eager), bitwise identical to the eager sequence."""
         loss = None
         K = self.GRAPH_STEPS
-        use_graph = self._state is not None and not self._ragged and os.environ.get("PACOH_GRAPH", "1") != "0"
         world, rank = getattr(self, "_world", 1), getattr(self, "_rank", 0)
+        # single rank only: a sharded run has an NCCL all-reduce in the step, and processes whose captured graphs hold NCCL
+        # kernels were seen to hang at process-group teardown (config #5 steps are tens of ms: launch overhead is irrelevant there)
+        use_graph = self._state is not None and not self._ragged and world == 1 and os.environ.get("PACOH_GRAPH", "1") != "0"
         while n > 0:
             lo, hi = eng.shard_bounds(self.task_batch_size, rank, world)
             if use_graph and n >= K and self._state.steps > 0 and self._idx_cur is not None and self._idx_cur.numel() == hi - lo:

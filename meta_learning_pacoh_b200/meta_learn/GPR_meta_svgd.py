@@ -163,7 +163,10 @@ class GPRegressionMetaLearnedSVGD(RegressionModelMetaLearned):
         numpy RandomState.choice draws, in the same order) from the device; PACOH_GRAPH=0 keeps every step eager.  Both
         forms launch the same kernels in the same order."""
         K = self.GRAPH_STEPS
-        use_graph = (self._state is not None and not self._ragged and os.environ.get("PACOH_GRAPH", "1") != "0")
+        # graphs only where no NCCL collective would sit inside the capture (single rank, or the peer-memory cross-rank sum):
+        # processes whose captured graphs hold NCCL kernels were seen to hang at process-group teardown
+        use_graph = (self._state is not None and not self._ragged and os.environ.get("PACOH_GRAPH", "1") != "0"
+                     and (self._world == 1 or self._peer is not None))
         while n > 0:
             if use_graph and n >= K and self._state.steps % 2 == 0 and self._state.steps > 0 and self._idx_cur is not None \
                     and self._idx_cur.numel() == self._local_batch():

@@ -82,3 +82,40 @@ def test_argument_validation_and_workspace_sizes():
 def test_engine_refuses_cpu_device():
     with pytest.raises(RuntimeError):
         eng.MetaMLLEngine(eng.GPArch(1), np.zeros((2, 5, 1), np.float32), np.zeros((2, 5), np.float32), device="cpu")
+
+
+def test_round2_entry_points_validate_arguments_and_size_workspaces():
+    """Host-side behaviour of the entry points added in round 2 (no device work): large-n layout, posterior workspace, step state."""
+    lib = _lib.lib
+    a = eng.GPArch(1, outputscale=True, noise_floor=1e-3).c_struct()
+    out = (ctypes.c_int64 * 14)()
+    # BASELINE config #5: 1024 tasks x 2048 points, P = 1 -> 16 tiles per side, one pass, factors = n^2 * 4 B per matrix
+    assert lib.pacoh_debug_big_layout(ctypes.byref(a), 1, 1024, 2048, out) == 0
+    off_big, nb, npad, batch, off_L, off_SB = out[0], out[1], out[2], out[3], out[4], out[5]
+    assert (nb, npad, batch) == (16, 2048, 1024) and off_L == 0 and off_SB >= 1024 * 2048 * 2048 * 4
+    total = lib.pacoh_workspace_bytes(ctypes.byref(a), 1, 1024, 2048)
+    assert off_big + out[13] <= total < 24 * 1024 ** 3
+    # n = 130: two tiles, padded to 256; n = 50: a small-matrix kernel, no large-n scratch at all
+    assert lib.pacoh_debug_big_layout(ctypes.byref(a), 2, 3, 130, out) == 0 and (out[1], out[2], out[3]) == (2, 256, 6)
+    assert lib.pacoh_debug_big_layout(ctypes.byref(a), 2, 3, 50, out) == 0 and list(out) == [0] * 14
+    # a batch that does not fit the 24 GB scratch budget is processed in passes
+    assert lib.pacoh_debug_big_layout(ctypes.byref(a), 4, 1024, 2048, out) == 0 and 1 <= out[3] < 4096
+    assert lib.pacoh_workspace_bytes(ctypes.byref(a), 4, 1024, 2048) < 26 * 1024 ** 3
+
+    # predictive path: context sets up to 128 points, n_c + n* up to 4096, the covariance scratch only on request
+    w0 = lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), 10, 20, 5, 50, 0)
+    w1 = lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), 10, 20, 5, 50, 1)
+    assert 0 < w0 < w1 and w1 - w0 >= 10 * 20 * 5 * 50 * 4
+    assert lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), 2, 3, 50, 500, 0) > 2 * 3 * 640 * 640 * 4      # joint sets > 64: Cholesky tiles
+    assert lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), 2, 3, 129, 10, 0) == _lib.PACOH_ERR_UNSUPPORTED
+    assert lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), 2, 3, 100, 4000, 0) == _lib.PACOH_ERR_UNSUPPORTED
+    assert lib.pacoh_gp_posterior_workspace_bytes(ctypes.byref(a), 0, 3, 5, 10, 0) == _lib.PACOH_ERR_INVALID
+    assert lib.pacoh_gp_posterior(ctypes.byref(a), 2, 3, 5, 10, None, None, None, None, None, None, None, None, None, None, None, None,
+                                  None, 0, None) == _lib.PACOH_ERR_INVALID
+    assert lib.pacoh_pred_metrics(2, 3, 10, None, None, None, None, None, 1.0, None, None) == _lib.PACOH_ERR_INVALID
+
+    # step state / fused optimizers: null pointers are refused before any launch
+    assert lib.pacoh_step_prepare(None, 1, 4, None, None, 0, None, None, 1e-3, 1.0, 0, 0.9, 0.999, None) == _lib.PACOH_ERR_INVALID
+    assert lib.pacoh_adam_step_dev(10, None, None, 1.0, None, None, 0.9, 0.999, 1e-8, None, None) == _lib.PACOH_ERR_INVALID
+    assert lib.pacoh_adamw_step_dev(10, None, None, 1.0, None, None, 0.9, 0.999, 1e-8, 0.1, None, None, None) == _lib.PACOH_ERR_INVALID
+    assert lib.pacoh_peer_allreduce_finalize_dev(9, 0, None, None, 0, None, None, 4, 10, None, None, None, 0.01, 0.5, None, None, None) == _lib.PACOH_ERR_INVALID

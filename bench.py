@@ -394,7 +394,9 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("config%d" % args.config, {}).get(dom)
+            # measured DRAM bytes of the dominant stage per step (ncu); the config-5 figure was taken at 2048 points per task
+            if args.config != 5 or args.points == 2048:
+                traffic = json.load(open(tpath)).get("config%d" % args.config, {}).get(dom)
         except Exception:
             traffic = None
     mp = {}

@@ -129,3 +129,22 @@ def test_persistent_backward_schedule_covers_every_tile_once():
         assert (seen == 1).all()
         assert per_cta <= max(6, 3 * 120 + 2)           # <= 120 tiles per warpgroup accumulator (3 warpgroups per CTA)
 
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores, a bounded slice of the workload) runs without a GPU and
+    prints ONE JSON line with the contract's keys; config 2 is the reference's own CPU-runnable shape."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "task-particle MLL+grad evals/s" and d["unit"] == "evals/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["config"]["config_id"] == 2 and d["config"]["evals_per_step"] == 200
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

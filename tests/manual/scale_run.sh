@@ -2,7 +2,7 @@
 CFG=${2:-4}
 for N in $1; do
   if [ "$N" = "1" ]; then CMD="python bench.py"; else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + N)) bench.py"; fi
-  timeout 900 $CMD --gpus $N --config $CFG --steps ${STEPS:-100} --warmup 10 --no-cpu-baseline $3 > gpurun_out/bench_r02_c${CFG}_n$N.json 2> gpurun_out/bench_r02_c${CFG}_n$N.err || tail -5 gpurun_out/bench_r02_c${CFG}_n$N.err
+  timeout ${LIMIT:-240} $CMD --gpus $N --config $CFG --steps ${STEPS:-100} --warmup 10 --no-cpu-baseline $3 > gpurun_out/bench_r02_c${CFG}_n$N.json 2> gpurun_out/bench_r02_c${CFG}_n$N.err || tail -5 gpurun_out/bench_r02_c${CFG}_n$N.err
   python - <<PY
 import json
 try:

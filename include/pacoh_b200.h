@@ -68,7 +68,10 @@ int64_t pacoh_param_count(const pacoh_arch_t* arch);
 int pacoh_hyper_prior_params(const pacoh_arch_t* arch, float weight_prior_std, float bias_prior_std,
                              float* mu_host, float* sigma_host);
 
-/* Scratch bytes needed by pacoh_meta_mll_fwd_bwd for P parameter vectors, T batch tasks of n points. */
+/* Scratch bytes needed by pacoh_meta_mll_fwd_bwd for P parameter vectors, T batch tasks of n points (n <= 4096; more than 4
+ * kernel features only for n <= 64).  Up to 64 points per task the matrices live on chip and the scratch holds the hand-over
+ * buffers between the MLP and GP kernels; above, it also holds the Cholesky factors of the blocked tensor-core path
+ * (~ 1.13 n^2 floats per (parameter vector, task), processed in passes of at most 24 GB: see pacoh_debug_big_layout). */
 int64_t pacoh_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t T, int32_t n);
 
 /*
@@ -76,7 +79,8 @@ int64_t pacoh_workspace_bytes(const pacoh_arch_t* arch, int32_t P, int32_t T, in
  * Replaces RandomGPMeta._log_prob_likelihood + autograd (random_gp.py:206-219, svgd.py:15-16,
  * GPR_meta_vi.py:221) and the PACOH-MAP loop body (GPR_meta_mll.py:109-113):
  *
- *   mll[p,t]      = log N(y_t | m_p(x_t), K_p(x_t,x_t) + sigma_p^2 I) / n
+ *   mll[p,t]      = log N(y_t | m_p(x_t), K_p(x_t,x_t) + sigma_p^2 I) / n        (dense Cholesky for every n: the reference's
+ *                   gpytorch switches to CG / Lanczos above settings.max_cholesky_size; parity is defined on the dense path)
  *   mll_sum[p]    = sum_t mll[p,t]                      (duplicates in task_idx count twice)
  *   dtheta_lik    = d mll_sum[p] / d theta[p,:]         (P, D)
  *

@@ -8,14 +8,19 @@
 //
 //   Khat = (s k + (sigma^2 + jitter) I) / tot,  tot = s + sigma^2 + jitter        (unit diagonal, rho = s / tot)
 //   Khat = L L^T                       left-looking, block column k:   C_ik = Khat_ik - sum_{j<k} L_ij L_kj^T
-//                                      diagonal tile: potrf + trtri in shared memory; panel: L_ik = C_ik L_kk^-T
-//   U = L^-T                           U_ab = -(sum_{j=a}^{b-1} U_aj L_bj^T) L_bb^-T        (wavefront over b - a)
-//   Khat^-1 = U U^T                    tile (a, b) = sum_{m >= max(a,b)} U_am U_bm^T, contracted on the fly with the
-//                                      Gram derivative (never stored):  w_ab = (beta_a alphahat_b - Khat^-1_ab) k_ab
-//   v = L^-1 r (inside the diagonal-tile kernel), alphahat = U v, quad = v.v / tot, log det = n log tot + 2 sum log L_ii
+//                                      diagonal tile: big_kernel<M_DIAG> writes C_kk, big_potrf_kernel factorises and inverts
+//                                      it in shared memory (potrf + trtri in place); panel: L_ik = C_ik L_kk^-T (fused solve)
+//   U = L^-T                           U_ab = -(sum_{j=a}^{b-1} U_aj L_bj^T) L_bb^-T        (one launch per distance b - a)
+//   Khat^-1 = U U^T                    lower block triangle only: tile (a, b <= a) = sum_{m >= a} U_am U_bm^T, contracted on the
+//                                      fly with the Gram derivative (never stored):  w_rc = (alphahat_r alphahat_c / tot -
+//                                      Khat^-1_rc) k_rc feeds the rows of block a directly and, for b < a, the rows of block b
+//                                      through column sums
+//   v = L^-1 r (block by block: the diagonal-tile kernels), alphahat = U v + one step of iterative refinement,
+//   quad = r . alphahat / tot, log det = n log tot + 2 sum log L_ii
 //
-// Every tile product is the same persistent, warp-specialised kernel (big_kernel<MODE>):
-//   warp 8  (one lane)  TMA producer: cp.async.bulk.tensor boxes of 128 rows x 32 fp32 (SWIZZLE_128B) into a 3-stage ring
+// Every tile product is the same persistent, warp-specialised kernel (big_kernel<MODE>, one CTA per SM, 212 KB shared memory,
+// all 512 tensor-memory columns):
+//   warp 8  (one lane)  TMA producer: cp.async.bulk.tensor boxes of 128 rows x 32 fp32 (SWIZZLE_128B) into a 4-stage ring
 //   warps 0-7           converters: the A rows go to TENSOR MEMORY as tf32 hi / lo parts (tcgen05.st), the B tile's lo part
 //                       is written beside the raw tile (which IS the hi operand: the tensor core truncates fp32 to tf32)
 //   warp 9  (one lane)  issues D[128 x 128] (+)= A B^T as 3 x 4 tcgen05.mma.kind::tf32 per 32-wide K chunk (lo.hi, hi.lo, hi.hi)
@@ -23,7 +28,8 @@
 //                       REGISTERS: the tensor core's accumulate truncates, so sums are kept short (48 MMAs) and the long
 //                       sum over K blocks is rounded to nearest on the CUDA cores.
 // The triangular solves with the diagonal tile are one more K block of the same pipeline whose A operand comes from the
-// register accumulator (C -> hi / lo -> tensor memory) and whose B operand is the inverted diagonal tile.
+// register accumulator (C -> hi / lo -> tensor memory) and whose B operand is the inverted diagonal tile; result tiles are
+// stored straight from the registers.
 #include <cuda.h>
 #include <math_constants.h>
 #include <algorithm>

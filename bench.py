@@ -373,8 +373,7 @@ def run_ours(args):
     d2h = P * 4 if cfg["kind"] == "svgd" else 4
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world, model)
         return
 
     # ---- roofline of the dominant kernel
@@ -443,8 +442,27 @@ def run_ours(args):
                                  "(%s); a replayed graph launches the same kernels" % (n_kern, n_own, ", ".join(own_names)[:600]),
             "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave(world, model)
+
+
+def leave(world, model=None):
+    """End of a rank's work.  Multi-rank: drop the captured step graph, tear the process group down under a watchdog and leave
+    without interpreter finalisation -- a teardown that hangs (seen once with NCCL kernels inside captured graphs) must not eat
+    the caller's time limit after the result line is already out.  Exit status 0 either way: the measurement is complete."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    watchdog = threading.Timer(45.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    if model is not None and getattr(model, "_graph", None) is not None:
+        model._graph = None
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    os._exit(0)
 
 
 def main():

@@ -349,7 +349,9 @@ def test_map_fused_adamw_equals_torch_adamw(ml, monkeypatch):
     lo, hi = a.arch.entries()["kernel_nn.out.bias"]
     keep = torch.ones(a.arch.D, dtype=torch.bool, device=a._flat.device)
     keep[lo:hi] = False
-    assert float((a._flat - b._flat)[0, keep].abs().max()) <= 1e-6          # measured 1.5e-8 after two steps (3e-3 moved)
+    # measured 1.5e-8 after two steps (3e-3 moved); the bound is far below what a wrong bias correction (~1e-3) or a missing
+    # decoupled decay (3 steps x lr x wd x |p| ~ 6e-5) would leave, with room for Adam's amplification of last-bit gradient noise
+    assert float((a._flat - b._flat)[0, keep].abs().max()) <= 1e-5
     assert float((a._mflat - b._mflat)[keep].abs().max()) <= 1e-6           # measured 6e-8
     assert float((a._vflat - b._vflat)[keep].abs().max()) <= 1e-6           # measured 2.5e-8
     moved = float((a._flat - ml.GPRegressionMetaLearned(train, weight_decay=0.2, random_seed=30)._flat)[0, keep].abs().max())

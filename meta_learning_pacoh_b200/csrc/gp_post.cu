@@ -77,8 +77,8 @@ __global__ void post_pack_kernel(const float* __restrict__ xc, const float* __re
 // One CTA per (test task, parameter vector), 256 threads, dynamic shared memory: two 128 x 132 tiles + vectors.
 __global__ void __launch_bounds__(256, 1) gp_post_kernel(PostArgs a) {
   extern __shared__ __align__(16) float sm[];
-  float* T = sm;                          // Khat_cc -> L -> Khat^-1
-  float* X = sm + NBP * LDT;              // U = L^-T, later the khat vectors of 128 test points
+  float* T = sm;                          // Khat_cc -> L (lower triangle, kept for the forward substitutions)
+  float* X = sm + NBP * LDT;              // U = L^-T (for v = U^T r), later the khat vectors of 128 test points
   float4* ucs = reinterpret_cast<float4*>(X + NBP * LDT);   // scaled context features
   float* rs = reinterpret_cast<float*>(ucs + NBP);          // residuals -> alphahat
   float* vs = rs + NBP;

@@ -119,3 +119,30 @@ def test_round2_entry_points_validate_arguments_and_size_workspaces():
     assert lib.pacoh_adam_step_dev(10, None, None, 1.0, None, None, 0.9, 0.999, 1e-8, None, None) == _lib.PACOH_ERR_INVALID
     assert lib.pacoh_adamw_step_dev(10, None, None, 1.0, None, None, 0.9, 0.999, 1e-8, 0.1, None, None, None) == _lib.PACOH_ERR_INVALID
     assert lib.pacoh_peer_allreduce_finalize_dev(9, 0, None, None, 0, None, None, 4, 10, None, None, None, 0.01, 0.5, None, None, None) == _lib.PACOH_ERR_INVALID
+
+
+@pytest.mark.parametrize("n", [65, 128, 129, 300, 512, 1000, 1024, 2047, 2048, 3000, 4096])
+def test_large_n_workspace_layout_invariants(n):
+    """Property sweep over the large-n scratch layout (host arithmetic only): tiles cover n, the sub-buffers are 256-byte
+    aligned, disjoint and in order, the per-pass batch respects the 24 GiB budget and never exceeds the matrices asked for,
+    and the caller-visible workspace size covers the layout for every batch size."""
+    lib = _lib.lib
+    a = eng.GPArch(1, outputscale=True, noise_floor=1e-3).c_struct()
+    out = (ctypes.c_int64 * 14)()
+    prev_total = 0
+    for P, T in ((1, 1), (1, 7), (3, 50), (1, 1024), (8, 4096)):
+        assert lib.pacoh_debug_big_layout(ctypes.byref(a), P, T, n, out) == 0
+        off_big, nb, npad, batch = out[0], out[1], out[2], out[3]
+        offs, total = list(out[4:13]), out[13]
+        assert nb == -(-n // 128) and npad == 128 * nb and npad >= n
+        assert 1 <= batch <= P * T
+        assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and offs == sorted(offs) and len(set(offs)) == len(offs)
+        assert offs[1] - offs[0] >= batch * npad * npad * 4                    # factor tiles of every matrix of a pass
+        assert offs[2] - offs[1] >= batch * nb * 2 * 128 * 128 * 4             # inverse diagonal tiles (L_kk^-1 and U_kk)
+        assert offs[-1] < total <= (24 << 30) + (64 << 20) or batch == 1       # budget (one matrix always goes through)
+        if batch < P * T:                                                      # passes: the budget is what limits the batch
+            assert (batch + 1) * (npad * npad * 4 + nb * 2 * 128 * 128 * 4) > (24 << 30) * 0.9
+        ws = lib.pacoh_workspace_bytes(ctypes.byref(a), P, T, n)
+        assert ws >= off_big + total and off_big % 256 == 0
+        assert total >= prev_total                                             # monotone in the number of matrices
+        prev_total = total
